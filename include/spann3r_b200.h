@@ -1,0 +1,115 @@
+/* spann3r_b200 -- C ABI of the B200-native Spann3R forward path (libspann3r_b200.so).
+ *
+ * The reference (HengyiWang/spann3r) is Python over PyTorch; its only native boundary is the
+ * pybind module `curope` (croco/models/curope/curope.cpp:49-69).  This header is the boundary a
+ * maintainer binds instead: flat extern "C" entry points, device pointers + sizes, an explicit
+ * cudaStream_t (as void*), int status returns (0 = ok, < 0 = error, text via s3r_last_error()).
+ * No torch types, no exceptions, no host synchronisation inside any call, nothing allocated that
+ * the caller must free except the opaque engine handle.
+ *
+ * Number format.  Every weight GEMM / convolution on the path consumes fp32 values carried as two
+ * bf16 planes (hi = bf16(x), lo = bf16(x - hi)) and issues three tcgen05 MMAs per product
+ * (DESIGN.md section 3).  "planes" below always means such a (hi, lo) pair of identical layout.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef SPANN3R_B200_H_
+#define SPANN3R_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3R_VERSION 100
+
+/* epilogue modes of s3r_gemm */
+enum { S3R_EPI_PLAIN = 0, S3R_EPI_PIXSHUF = 1, S3R_EPI_QKV = 2, S3R_EPI_HEADTAIL = 3 };
+enum { S3R_ACT_NONE = 0, S3R_ACT_GELU = 1, S3R_ACT_RELU = 2 };
+
+int s3r_version(void);
+/* last error text of the calling thread ("" if none) */
+const char* s3r_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is visible, else 0 (never falls back to CPU) */
+int s3r_device_ok(void);
+
+/* ---- op level ------------------------------------------------------------------------------ */
+
+/* fp32 [rows, c] (row stride ldx) -> planes [rows, ldp] at column col0, optional ReLU first.
+ * Replaces nothing in the reference; it is the format conversion at the head of a GEMM chain. */
+int s3r_split(const float* x, int64_t ldx, void* hi, void* lo, int64_t ldp, int col0, int64_t rows, int c, int relu,
+              void* stream);
+
+/* nn.LayerNorm over the last dim (c = 768 or 1024), fp32 and/or planes out.
+ * croco/models/blocks.py:116-130,176-191 (norm1/2/3/norm_y, eps 1e-6), dust3r/model.py:151,203
+ * (enc_norm, dec_norm), spann3r/model.py:245-247 (norm_q/k/v, eps 1e-5).
+ * Groups: row r uses weight set (r / rows_per_group) at w + set*wb_group_stride (0 = one set).
+ * swap_rows > 0: two groups of swap_rows rows; output rows and weight sets are exchanged between
+ * the groups (the twin decoders' norm_y, dust3r/model.py:197-199). */
+int s3r_layernorm(const float* x, int64_t ldx, const float* w, const float* b, int64_t wb_group_stride,
+                  int64_t rows_per_group, float eps, int64_t rows, int c, float* out, int64_t ldo, void* hi, void* lo,
+                  int64_t ldp, int col0, int64_t swap_rows, void* stream);
+
+/* In-place 2-D RoPE, drop-in for curope.rope_2d(tokens[B,N,H,D], pos[B,N,2] int64, base, fwd)
+ * (croco/models/curope/curope.cpp:49-65, kernels.cu:18-81); fp32 tokens, D contiguous, strides in
+ * elements.  Unlike the reference kernel it runs on the given stream, not the legacy stream 0. */
+int s3r_rope2d_inplace(float* tokens, const int64_t* pos, int64_t bn, int h, int d, int64_t stride_tok,
+                       int64_t stride_head, float base, float fwd, void* stream);
+
+/* Patch im2col for Conv2d(3, E, k=16, s=16): img with element strides (sb, sc, sy, sx) ->
+ * planes [b*gh*gw, 768], k = c*256 + i*16 + j.  dust3r/patch_embed.py:19-29. */
+int s3r_im2col_patch16(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int b, int gh, int gw,
+                       void* hi, void* lo, void* stream);
+/* im2col for Conv2d(C, C, 3, stride 2, pad 1): planes [nb,h,w,c] -> planes [nb*ho*wo, 9*c].
+ * croco/models/dpt_block.py:396-408 (act_4_postprocess). */
+int s3r_im2col_3x3s2(const void* ihi, const void* ilo, int nb, int h, int w, int c, int ho, int wo, void* ohi,
+                     void* olo, void* stream);
+/* Bilinear x2, align_corners=True, channels-last fp32 [nb,h,w,c] -> fp32 and/or planes [nb,2h,2w,c].
+ * croco/models/dpt_block.py:214-215, 246-253. */
+int s3r_upsample2x(const float* x, int nb, int h, int w, int c, float* out, void* hi, void* lo, void* stream);
+
+/* The tensor-core workhorse: D = A * B^T with fused epilogue (see EPI modes).
+ *   A planes [groups*nb, h, w, kc] (a linear layer is h = 1, w = rows), B planes [groups*n, taps, kc],
+ *   taps = 1 (linear / 1x1 conv / ConvTranspose with kernel == stride) or 9 (3x3, stride 1, pad 1).
+ * Replaces nn.Linear / Conv2d / ConvTranspose2d calls of croco/models/blocks.py:73-79,94-112,149-169,
+ * dust3r/model.py:189-190, spann3r/model.py:250-261,310 and croco/models/dpt_block.py (all convs). */
+typedef struct s3r_gemm_desc {
+  const void* a_hi; const void* a_lo;
+  const void* b_hi; const void* b_lo;
+  int groups, nb, h, w, kc, taps, n;
+  int epi, act, plane_relu, force_bn;
+  const float* bias;                       /* [groups*n] (PIXSHUF: [groups*ps_cout]) or NULL */
+  const float* res1; int64_t ldr1;         /* optional residual adds, indexed like out_f32 */
+  const float* res2; int64_t ldr2;
+  float* out_f32; int64_t ldo;             /* optional fp32 output [groups*rows, ldo] */
+  void* out_hi; void* out_lo; int64_t ldp; int plane_col0;   /* optional planes output */
+  /* S3R_EPI_PIXSHUF: ConvTranspose2d(kernel == stride == ps_s), n = ps_s*ps_s*ps_cout, col = (i, j, co) */
+  int ps_s, ps_cout;
+  /* S3R_EPI_QKV: columns are q_c-wide roles starting at q_role_base (0 q, 1 k, 2 v); q,k get 2-D RoPE
+   * from q_pos ([groups*rows, 2] int32 (y, x)) and the (cos, sin) table q_cs [maxpos, 16, 2]; q is scaled by
+   * q_scale; outputs q_out/k_out [groups*q_nb, heads, q_ntok, 64], vt_out [groups*q_nb, heads, 64, q_ntok_pad],
+   * all rounded to tf32.  croco/models/blocks.py:97-104,154-160 + models/pos_embed.py:112-159. */
+  int q_c, q_role_base, q_ntok, q_ntok_pad, q_rope, q_nb;
+  const int32_t* q_pos; const float* q_cs;
+  float* q_out; float* k_out; float* vt_out; float q_scale;
+  /* S3R_EPI_HEADTAIL (n == 128): ReLU -> Conv2d(128, 4, 1) (ht_w [groups,4,128], ht_b [groups,4]) ->
+   * postprocess: pts3d = xyz/|xyz| * expm1(|xyz|), conf = 1 + exp(x3).
+   * croco/models/dpt_block.py:318-324, dust3r/heads/postprocess.py:10-58. */
+  const float* ht_w; const float* ht_b; float* ht_pts; float* ht_conf;
+} s3r_gemm_desc;
+int s3r_gemm(const s3r_gemm_desc* d, void* stream);
+/* tile width the planner would pick (64/128/256), for tests */
+int s3r_gemm_tile_n(const s3r_gemm_desc* d);
+
+/* Fused multi-head attention core, head dim 64: O = softmax(Q K^T) V per (batch*head) on tf32 tcgen05.
+ *   q [bh, nq, 64], k [bh, nk, 64] (already RoPE'd / scaled by the QKV epilogue), vt [bh, 64, nk_pad];
+ *   output [b*nq, heads*64] as planes and/or fp32 (row stride ldo).
+ * croco/models/blocks.py:106-110 (self), :162-166 (cross). */
+int s3r_attention(const float* q, const float* k, const float* vt, int bh, int heads, int nq, int nk, int nk_pad,
+                  void* o_hi, void* o_lo, float* o_f32, int64_t ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPANN3R_B200_H_ */

@@ -1,0 +1,75 @@
+// Host-visible description of one launch of the split-bf16 tcgen05 GEMM / implicit-GEMM conv engine.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s3r {
+
+enum EpiMode : int {
+  EPI_PLAIN = 0,      // out[row, col]
+  EPI_PIXSHUF = 1,    // ConvTranspose2d with kernel == stride: col=(i,j,co) scatters to pixel (h*s+i, w*s+j)
+  EPI_QKV = 2,        // q/k/v head split (+ 2-D RoPE on q,k; q pre-scaled; v stored transposed), tf32-rounded
+  EPI_HEADTAIL = 3,   // DPT head tail: ReLU -> 1x1 conv (128->4) -> postprocess (pts3d, conf)
+};
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+// A operand: activations as two bf16 planes laid out [G*NB, H, W, C] (C contiguous).  A plain
+// linear layer is the degenerate image H=1, W=rows.  B operand: weights as two bf16 planes laid
+// out [G*N, taps, Kc] (Kc contiguous).  Groups (G) share every shape and differ only in data.
+struct GemmArgs {
+  alignas(64) CUtensorMap tmA_hi;
+  alignas(64) CUtensorMap tmA_lo;
+  alignas(64) CUtensorMap tmB_hi;
+  alignas(64) CUtensorMap tmB_lo;
+  // geometry
+  int groups;
+  int W, H, NB;        // pixel space of one group
+  int bw, bh;          // tile box, bw*bh == 128
+  int tiles_w, tiles_h;
+  int N;               // output columns per group
+  int Kc, taps, kpt;   // channels per tap, 1 or 9 taps, k-blocks (of 64) per tap
+  // epilogue
+  int epi, act, plane_relu;
+  const float* bias;   // [G*N] (EPI_PIXSHUF: [G*Cout]) or null
+  const float* res1; int ldr1;
+  const float* res2; int ldr2;
+  float* out_f32; int ldo;            // row stride in elements
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldp; int plane_col0;
+  long long out_group_rows;           // rows of `out`/`res`/planes per group
+  // EPI_PIXSHUF
+  int ps_s, ps_cout;
+  // EPI_QKV
+  int q_C, q_role_base, q_ntok, q_ntok_pad, q_rope, q_nb;   // q_nb: batch items per group
+  const int* q_pos;        // [G*rows, 2] (y, x) per A row
+  const float2* q_cs;      // [maxpos, 16] (cos, sin)
+  float* q_out; float* k_out; float* vt_out;
+  float q_scale;
+  // EPI_HEADTAIL
+  const float* ht_w;       // [G, 4, 128]
+  const float* ht_b;       // [G, 4]
+  float* ht_pts;           // [G*rows, 3]
+  float* ht_conf;          // [G*rows]
+};
+
+struct GemmPlan {
+  GemmArgs args;
+  dim3 grid;
+  int bn;          // 64 / 128 / 256
+  double flops;    // algorithmic 2*M*N*K (all groups), for roofline accounting
+};
+
+// Encodes the four tensor maps and picks the tile shape.  Returns 0 or a negative error.
+int gemm_plan_init(GemmPlan* plan,
+                   const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,   // [G*NB, H, W, Kc]
+                   const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,   // [G*N, taps, Kc]
+                   int groups, int NB, int H, int W, int Kc, int taps, int N, int force_bn = 0);
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box);
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace s3r

@@ -1,0 +1,29 @@
+// Launchers of the non-GEMM kernels (definitions in elementwise.cu, attention.cu, memory.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "gemm.cuh"
+
+namespace s3r {
+
+int launch_split(const float* x, long long ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ldp, int col0,
+                 long long rows, int C, int relu, cudaStream_t st);
+int launch_layernorm(const float* x, long long ldx, const float* w, const float* b, long long wb_group_stride,
+                     long long rows_per_group, float eps, long long rows, int C, float* out, long long ldo,
+                     __nv_bfloat16* hi, __nv_bfloat16* lo, long long ldp, int col0, long long swap_rows,
+                     cudaStream_t st);
+int launch_im2col_patch16(const float* img, long long sb, long long sc, long long sy, long long sx, int B, int gh,
+                          int gw, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+int launch_im2col_3x3s2(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, int NB, int H, int W, int C, int Ho, int Wo,
+                        __nv_bfloat16* ohi, __nv_bfloat16* olo, cudaStream_t st);
+int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                      cudaStream_t st);
+int launch_rope2d(float* tokens, const long long* pos, long long BN, int H, int D, long long stride_tok,
+                  long long stride_head, float base, float fwd, cudaStream_t st);
+
+// fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output
+int launch_attention(const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk, int nk_pad,
+                     __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo, cudaStream_t st);
+
+}  // namespace s3r

@@ -1,0 +1,158 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by running the REAL reference (CPU, strict fp32).
+
+Runs only in the authoring container (needs /root/reference, which does not exist on the
+GPU box).  Nothing under tests/, bench.py or smoke() imports this file; they read the small
+fixtures it writes into tests/golden/.
+
+    python tools/make_golden.py            # everything (~10 min on 8 cores)
+    python tools/make_golden.py --only spec
+
+Outputs
+  tests/golden/state_dict_spec.json   key -> shape of the reference Spann3R state dict
+  tests/golden/cfg1_224_2f_raw.npz    BASELINE config 1 (2 x 224x224), raw random-init weights
+  tests/golden/seq_224_4f_sharp.npz   4 x 224x224, sharpened weights (two memory reads)
+  tests/golden/seq_384x512_3f_sharp.npz  3 x 384x512, sharpened, outputs sub-sampled (::4, ::4)
+Each npz also holds sub-sampled per-stage activations captured with forward hooks so that a
+parity failure can be localised to a stage.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+GOLD = os.path.join(REPO, "tests", "golden")
+
+
+def build_reference(seed=0, sharpen=False):
+    sys.path.insert(0, REF)
+    torch.serialization.add_safe_globals([argparse.Namespace])
+    from spann3r.model import Spann3R  # noqa  (reference)
+    from spann3r_b200 import synth
+
+    spec_path = os.path.join(GOLD, "state_dict_spec.json")
+    tmp = "/tmp/fake_dust3r.pth"
+    if not os.path.exists(spec_path):
+        # bootstrap: build once with whatever init to learn the key inventory
+        from dust3r.model import AsymmetricCroCo3DStereo  # noqa
+        inf = float("inf")  # noqa
+        net = eval(synth.DUST3R_ARGS.replace("ManyAR_PatchEmbed", "PatchEmbedDust3R"))
+        torch.save({"args": argparse.Namespace(model=synth.DUST3R_ARGS), "model": net.state_dict()}, tmp)
+        m = Spann3R(dus3r_name=tmp, use_feat=False)
+        spec = {"spann3r": {k: list(v.shape) for k, v in m.state_dict().items()},
+                "reference_commit": "f89d6a23", "torch": torch.__version__}
+        with open(spec_path, "w") as f:
+            json.dump(spec, f, indent=0)
+        print("wrote", spec_path, len(spec["spann3r"]), "keys")
+    spec = synth.load_spec(spec_path)
+    dust3r_sd = synth.make_state_dict(spec, seed=seed, prefix="dust3r.")
+    torch.save({"args": argparse.Namespace(model=synth.DUST3R_ARGS), "model": dust3r_sd}, tmp)
+    t0 = time.time()
+    m = Spann3R(dus3r_name=tmp, use_feat=False)
+    sd = synth.make_state_dict(spec, seed=seed, sharpen=sharpen)
+    missing = m.load_state_dict(sd, strict=True)
+    print("reference built in %.1fs" % (time.time() - t0), missing)
+    return m.eval()
+
+
+def sub(t, tok_stride=7, ch_stride=8):
+    t = t.detach().float()
+    if t.ndim == 3:      # [B, N, C] tokens
+        return t[:, ::tok_stride, ::ch_stride].contiguous().numpy()
+    if t.ndim == 4:      # [B, C, H, W] feature map
+        return t[:, ::ch_stride, ::3, ::3].contiguous().numpy()
+    return t.numpy()
+
+
+def run(model, frames, out_path, px_stride=1, hooks=True):
+    acts = {}
+    handles = []
+    if hooks:
+        watch = {
+            "dust3r.patch_embed": lambda o: o[0],
+            "dust3r.enc_blocks.0": lambda o: o,
+            "dust3r.enc_blocks.23": lambda o: o,
+            "dust3r.enc_norm": lambda o: o,
+            "dust3r.decoder_embed": lambda o: o,
+            "dust3r.dec_blocks.0": lambda o: o[0],
+            "dust3r.dec_blocks2.0": lambda o: o[0],
+            "dust3r.dec_blocks.11": lambda o: o[0],
+            "dust3r.dec_blocks2.11": lambda o: o[0],
+            "attn_head_1": lambda o: o,
+            "attn_head_2": lambda o: o,
+            "dust3r.downstream_head1.dpt.act_postprocess.0": lambda o: o,
+            "dust3r.downstream_head1.dpt.act_postprocess.3": lambda o: o,
+            "dust3r.downstream_head1.dpt.scratch.refinenet4": lambda o: o,
+            "dust3r.downstream_head1.dpt.scratch.refinenet1": lambda o: o,
+            "dust3r.downstream_head1.dpt": lambda o: o,
+            "pos_patch_embed": lambda o: o[0],
+            "value_encoder.5": lambda o: o,
+            "value_out": lambda o: o,
+        }
+        mods = dict(model.named_modules())
+        for name, pick in watch.items():
+            def mk(name, pick):
+                def hook(_m, _i, o):
+                    k = "act/" + name
+                    n = sum(1 for kk in acts if kk.startswith(k + "#"))
+                    acts[f"{k}#{n}"] = sub(pick(o))
+                return hook
+            handles.append(mods[name].register_forward_hook(mk(name, pick)))
+    t0 = time.time()
+    with torch.no_grad():
+        preds, preds_all, mem = model(frames, return_memory=True)
+    dt = time.time() - t0
+    for h in handles:
+        h.remove()
+    out = {}
+    s = px_stride
+    for i, p in enumerate(preds):
+        for k, v in p.items():
+            out[f"preds/{i}/{k}"] = v[:, ::s, ::s].contiguous().numpy()
+    for i, (r1, r2) in enumerate(preds_all):
+        for k, v in r2.items():
+            out[f"preds_all/{i}/res2/{k}"] = v[:, ::s, ::s].contiguous().numpy()
+    out["mem/mem_k_sub"] = sub(mem.mem_k)
+    out["mem/mem_v_sub"] = sub(mem.mem_v)
+    out["mem/mem_attn"] = mem.mem_attn.numpy()
+    out["mem/mem_count"] = mem.mem_count.numpy()
+    out["meta/px_stride"] = np.array(s)
+    out["meta/ref_seconds"] = np.array(dt)
+    out["meta/threads"] = np.array(torch.get_num_threads())
+    finite = all(np.isfinite(v).all() for k, v in out.items() if k.startswith("preds"))
+    out.update(acts)
+    np.savez_compressed(out_path, **out)
+    print(f"wrote {out_path}: {dt:.1f}s ref forward, finite={finite}, "
+          f"|pts3d| max {max(np.abs(v).max() for k, v in out.items() if 'pts3d' in k):.3g}, "
+          f"{os.path.getsize(out_path)/1e6:.2f} MB")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="all")
+    args = ap.parse_args()
+    from spann3r_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    os.makedirs(GOLD, exist_ok=True)
+    if args.only in ("all", "spec", "cfg1"):
+        m = build_reference(sharpen=False)
+        if args.only != "spec":
+            run(m, synth.make_frames(2, 224, 224), os.path.join(GOLD, "cfg1_224_2f_raw.npz"))
+        del m
+    if args.only in ("all", "seq224", "seq512"):
+        m = build_reference(sharpen=True)
+        if args.only in ("all", "seq224"):
+            run(m, synth.make_frames(4, 224, 224), os.path.join(GOLD, "seq_224_4f_sharp.npz"))
+        if args.only in ("all", "seq512"):
+            run(m, synth.make_frames(3, 384, 512), os.path.join(GOLD, "seq_384x512_3f_sharp.npz"), px_stride=4)
+
+
+if __name__ == "__main__":
+    main()
