@@ -109,6 +109,86 @@ int s3r_gemm_tile_n(const s3r_gemm_desc* d);
 int s3r_attention(const float* q, const float* k, const float* vt, int bh, int heads, int nq, int nk, int nk_pad,
                   void* o_hi, void* o_lo, float* o_f32, int64_t ldo, void* stream);
 
+/* ---- model level: the per-frame forward path -------------------------------------------------
+ * Packed weights.  The host (spann3r_b200/weights.py) converts the reference state dict ONCE into
+ * split-bf16 planes laid out [groups*N, taps*Kc] (K contiguous) plus fp32 biases / LayerNorm params,
+ * and hands the engine a table of device pointers; the engine never sees parameter names.
+ * "Grouped" entries stack two weight sets that run as one launch: the twin decoders
+ * (dust3r.dec_blocks / dec_blocks2, dust3r/model.py:194-200), the two key heads (attn_head_1/2)
+ * and the two DPT heads (downstream_head1/2). */
+typedef struct s3r_planes { const void* hi; const void* lo; } s3r_planes;
+typedef struct s3r_ln { const float* w; const float* b; } s3r_ln;      /* grouped: [G, C] contiguous */
+typedef struct s3r_lin { s3r_planes w; const float* b; } s3r_lin;      /* b may be NULL */
+
+typedef struct s3r_block_w {       /* croco/models/blocks.py:114-130 */
+  s3r_ln norm1; s3r_lin qkv; s3r_lin proj; s3r_ln norm2; s3r_lin fc1; s3r_lin fc2;
+} s3r_block_w;
+typedef struct s3r_decblock_w {    /* croco/models/blocks.py:171-191, two streams as 2 groups; kv = [projk; projv] */
+  s3r_ln norm1; s3r_lin qkv; s3r_lin proj; s3r_ln norm_y; s3r_ln norm2; s3r_lin q; s3r_lin kv; s3r_lin cproj;
+  s3r_ln norm3; s3r_lin fc1; s3r_lin fc2;
+} s3r_decblock_w;
+typedef struct s3r_rcu_w { s3r_lin conv1; s3r_lin conv2; } s3r_rcu_w;                 /* dpt_block.py:121-142 */
+typedef struct s3r_fusion_w { s3r_rcu_w rcu1; s3r_rcu_w rcu2; s3r_lin out_conv; } s3r_fusion_w; /* :189-218 */
+typedef struct s3r_dpt_w {         /* dust3r/heads/dpt_head.py:34-65; both heads as 2 groups */
+  s3r_lin act1_conv, act1_up, act2_conv, act2_up, act3_conv, act4_conv, act4_down;
+  s3r_lin layer_rn[4];
+  s3r_fusion_w refine[4];          /* refine[i] = scratch.refinenet{i+1} */
+  s3r_lin head0, head2;
+  const float* head4_w;            /* [2, 4, 128] */
+  const float* head4_b;            /* [2, 4] */
+} s3r_dpt_w;
+typedef struct s3r_model_w {
+  s3r_lin patch_embed; s3r_block_w enc[24]; s3r_ln enc_norm;
+  s3r_lin decoder_embed; s3r_decblock_w dec[12]; s3r_ln dec_norm;
+  s3r_lin key_fc1, key_fc2;
+  s3r_dpt_w dpt;
+  s3r_lin pos_patch_embed; s3r_block_w val[6]; s3r_ln value_norm; s3r_lin value_out;
+  s3r_ln norm_q, norm_k, norm_v;
+  const float* rope_cs;            /* [rope_maxpos, 16, 2] (cos, sin), models/pos_embed.py:120-129 */
+  int rope_maxpos;
+} s3r_model_w;
+
+/* The spatial-memory bank of one batch of sequences (spann3r/model.py:11-95), caller-owned buffers.
+ * Keys / values are kept pre-normalised (LN_k / LN_v applied at write time) as planes for the read
+ * GEMMs, plus the raw fp32 rows (similarity gate, return_memory). */
+typedef struct s3r_bank {
+  void* kn_hi; void* kn_lo;        /* [B, cap, 1024] */
+  void* vnt_hi; void* vnt_lo;      /* [B, 1024, cap]  (transposed) */
+  float* k_raw; float* v_raw;      /* [B, cap, 1024] */
+  float* attn; float* count;       /* [B, cap] */
+  int cap;                         /* multiple of 8 */
+  int len;                         /* tokens currently stored */
+} s3r_bank;
+
+typedef struct s3r_engine s3r_engine;
+/* One engine per (device, batch of sequences, image size).  Allocates its own activation workspace
+ * (freed by destroy); `max_images` bounds the images one encode call may batch (>= 2*batch). */
+s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int width, int max_images);
+void s3r_engine_destroy(s3r_engine* e);
+/* dust3r/model.py:131-154 _encode_image: img [nimg,3,H,W] fp32 -> feat [nimg, N, 1024] fp32 */
+int s3r_engine_encode(s3r_engine* e, const float* img, int nimg, float* feat, void* stream);
+/* dust3r/model.py:186-205 _decoder on (f1, f2) [B,N,1024]; hooks stay inside the engine for
+ * keyheads()/heads(); dec_all (nullable) receives all 12 layer outputs [12, 2, B*N, 768] (last one normed). */
+int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* dec_all, void* stream);
+/* spann3r/model.py:299-303 encode_feat_key for both heads: cat(feat_i, dec_i[-1]) -> [B,N,1024] */
+int s3r_engine_keyheads(s3r_engine* e, const float* feat1, const float* feat2, float* k1, float* k2, void* stream);
+/* dust3r/model.py:207-211 + heads/dpt_head.py + postprocess.py: pts [2,B,H,W,3], conf [2,B,H,W] */
+int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream);
+/* spann3r/model.py:305-320 encode_cur_value, plus the `cur_v + feat_k1` of :519-521: out [B,N,1024] */
+int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, float* out, void* stream);
+/* spann3r/model.py:145-183 memory_read (eval: thresh = 5e-4; 0 disables): out = attn.V + feat; bank.attn += colsum */
+int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float* out,
+                           void* stream);
+/* spann3r/model.py:80-95 add_mem: append N tokens at bank.len (caller then sets len += N) */
+int s3r_engine_memory_append(s3r_engine* e, const s3r_bank* bank, const float* feat_k, const float* feat_v,
+                             void* stream);
+/* spann3r/model.py:97-118 check_sim: out[b, t] = mean cosine vs each of the last wm frames (device array [B, wm]) */
+int s3r_engine_check_sim(s3r_engine* e, const s3r_bank* bank, const float* feat_k, int wm, float* out, void* stream);
+/* algorithmic FLOPs (2*M*N*K of every tensor-core launch) issued since the last call; resets the counter */
+double s3r_engine_take_flops(s3r_engine* e);
+/* number of kernel launches since the last call; resets the counter */
+long long s3r_engine_take_launches(s3r_engine* e);
+
 #ifdef __cplusplus
 }
 #endif

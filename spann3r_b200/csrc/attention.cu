@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <cstring>
+
 namespace s3r {
 
 namespace attn {
@@ -34,16 +36,6 @@ constexpr uint32_t TMEM_COLS = 512;       // S0 [0,128) S1 [128,256) O [256,320)
 constexpr int kThreads = 192;
 }  // namespace attn
 
-struct AttnArgs {
-  alignas(64) CUtensorMap tmQ;   // (64, nq, BH)  box (32,128,1)
-  alignas(64) CUtensorMap tmK;   // (64, nk, BH)  box (32,128,1)
-  alignas(64) CUtensorMap tmV;   // (nk, 64, BH)  box (32, 64,1), row stride nk_pad
-  int nq, nk, heads;
-  __nv_bfloat16* o_hi;
-  __nv_bfloat16* o_lo;
-  float* o_f32;
-  long long ldo;
-};
 
 __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
   using namespace attn;
@@ -270,16 +262,15 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
   }
 }
 
-int launch_attention(const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk, int nk_pad,
-                     __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo, cudaStream_t st) {
+int attn_plan_init(AttnPlan* plan, const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk,
+                   int nk_pad) {
   using namespace attn;
-  if (nq <= 0 || nk <= 0 || BH <= 0) return 0;
+  memset(plan, 0, sizeof(*plan));
   if (nk_pad % 4 != 0 || nk_pad < nk) {
     set_error("attention: nk_pad=%d must be >= nk=%d and a multiple of 4", nk_pad, nk);
     return -1;
   }
-  AttnArgs a;
-  memset(&a, 0, sizeof(a));
+  AttnArgs& a = plan->args;
   {
     uint64_t dims[3] = {64, (uint64_t)nq, (uint64_t)BH};
     uint64_t str[2] = {64 * 4, (uint64_t)nq * 64 * 4};
@@ -302,7 +293,14 @@ int launch_attention(const float* q, const float* k, const float* vt, int BH, in
     if (r) return r;
   }
   a.nq = nq; a.nk = nk; a.heads = heads;
-  a.o_hi = o_hi; a.o_lo = o_lo; a.o_f32 = o_f32; a.ldo = ldo;
+  plan->grid = dim3((nq + BQ - 1) / BQ, BH);
+  plan->flops = 4.0 * BH * (double)nq * nk * 64;
+  return 0;
+}
+
+int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo,
+                cudaStream_t st) {
+  using namespace attn;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -312,14 +310,24 @@ int launch_attention(const float* q, const float* k, const float* vt, int BH, in
     }
     attr_set = true;
   }
-  dim3 grid((nq + BQ - 1) / BQ, BH);
-  attention_kernel<<<grid, kThreads, SMEM, st>>>(a);
+  AttnArgs a = plan.args;
+  a.o_hi = o_hi; a.o_lo = o_lo; a.o_f32 = o_f32; a.ldo = ldo;
+  attention_kernel<<<plan.grid, kThreads, SMEM, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("attention launch failed: %s", cudaGetErrorString(e));
     return -6;
   }
   return 0;
+}
+
+int launch_attention(const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk, int nk_pad,
+                     __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo, cudaStream_t st) {
+  if (nq <= 0 || nk <= 0 || BH <= 0) return 0;
+  AttnPlan plan;
+  int r = attn_plan_init(&plan, q, k, vt, BH, heads, nq, nk, nk_pad);
+  if (r) return r;
+  return attn_launch(plan, o_hi, o_lo, o_f32, ldo, st);
 }
 
 }  // namespace s3r

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         const int nb = mt / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.bw, h0 = th * args.bh;
         const int img = g * args.NB + nb;
-        const int brow = g * args.N + nt * BN;
+        const int brow = g * args.b_group_rows + nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / args.kpt;
           const int kc = (kb - tap * args.kpt) * BK;
@@ -446,14 +446,18 @@ static int num_sms() {
 
 int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
                    const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, int groups, int NB, int H, int W, int Kc,
-                   int taps, int N, int force_bn) {
+                   int taps, int N, int force_bn, long long lda, long long ldb, long long b_group_rows) {
   memset(plan, 0, sizeof(*plan));
   GemmArgs& a = plan->args;
-  if (Kc % 8 != 0 || N % 32 != 0 || (taps != 1 && taps != 9)) {
-    set_error("gemm_plan_init: unsupported shape Kc=%d N=%d taps=%d (need Kc%%8==0, N%%32==0, taps in {1,9})", Kc, N,
-              taps);
+  if (lda == 0) lda = Kc;
+  if (ldb == 0) ldb = (long long)Kc * taps;
+  if (b_group_rows == 0) b_group_rows = N;
+  if (lda % 8 != 0 || ldb % 8 != 0 || (taps != 1 && taps != 9) || (taps == 9 && Kc % 8 != 0)) {
+    set_error("gemm_plan_init: unsupported shape Kc=%d N=%d taps=%d lda=%lld ldb=%lld (row strides must be multiples "
+              "of 8 elements, taps in {1,9})", Kc, N, taps, lda, ldb);
     return -1;
   }
+  a.b_group_rows = (int)b_group_rows;
   a.W = W; a.H = H; a.NB = NB; a.N = N; a.Kc = Kc; a.taps = taps;
   a.kpt = (Kc + BK - 1) / BK;
   a.bw = W >= 128 ? 128 : next_pow2(W);
@@ -473,15 +477,16 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   const uint64_t esz = 2;
   {
     uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)W, (uint64_t)H, (uint64_t)NB * groups};
-    uint64_t str[3] = {(uint64_t)Kc * esz, (uint64_t)Kc * W * esz, (uint64_t)Kc * W * H * esz};
+    uint64_t str[3] = {(uint64_t)lda * esz, (uint64_t)lda * W * esz, (uint64_t)lda * W * H * esz};
     uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.bw, (uint32_t)a.bh, 1};
     int r;
     if ((r = encode_tmap(&a.tmA_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a_hi, dims, str, box))) return r;
     if ((r = encode_tmap(&a.tmA_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a_lo, dims, str, box))) return r;
   }
   {
-    uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)taps, (uint64_t)N * groups};
-    uint64_t str[2] = {(uint64_t)Kc * esz, (uint64_t)Kc * taps * esz};
+    uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)taps, (uint64_t)(b_group_rows * (groups - 1) + N)};
+    // with a single tap the tap stride is never used, but must still be a multiple of 16 bytes
+    uint64_t str[2] = {(uint64_t)(taps == 1 ? ldb : Kc) * esz, (uint64_t)ldb * esz};
     uint32_t box[3] = {(uint32_t)BK, 1, (uint32_t)bn};
     int r;
     if ((r = encode_tmap(&a.tmB_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, b_hi, dims, str, box))) return r;

@@ -30,6 +30,7 @@ struct GemmArgs {
   int tiles_w, tiles_h;
   int N;               // output columns per group
   int Kc, taps, kpt;   // channels per tap, 1 or 9 taps, k-blocks (of 64) per tap
+  int b_group_rows;    // B rows between groups
   // epilogue
   int epi, act, plane_relu;
   const float* bias;   // [G*N] (EPI_PIXSHUF: [G*Cout]) or null
@@ -61,10 +62,13 @@ struct GemmPlan {
 };
 
 // Encodes the four tensor maps and picks the tile shape.  Returns 0 or a negative error.
+// lda / ldb: row strides (elements) of A pixels / B rows (0 = dense: Kc resp. taps*Kc);
+// b_group_rows: rows between consecutive groups of B (0 = N).
 int gemm_plan_init(GemmPlan* plan,
                    const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,   // [G*NB, H, W, Kc]
                    const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,   // [G*N, taps, Kc]
-                   int groups, int NB, int H, int W, int Kc, int taps, int N, int force_bn = 0);
+                   int groups, int NB, int H, int W, int Kc, int taps, int N, int force_bn = 0,
+                   long long lda = 0, long long ldb = 0, long long b_group_rows = 0);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,

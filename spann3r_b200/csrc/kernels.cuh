@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "gemm.cuh"
+#include <cuda.h>
 
 namespace s3r {
 
@@ -21,6 +22,36 @@ int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, _
                       cudaStream_t st);
 int launch_rope2d(float* tokens, const long long* pos, long long BN, int H, int D, long long stride_tok,
                   long long stride_head, float base, float fwd, cudaStream_t st);
+
+struct AttnArgs {
+  alignas(64) CUtensorMap tmQ;   // (64, nq, BH)  box (32,128,1)
+  alignas(64) CUtensorMap tmK;   // (64, nk, BH)  box (32,128,1)
+  alignas(64) CUtensorMap tmV;   // (nk, 64, BH)  box (32, 64,1), row stride nk_pad
+  int nq, nk, heads;
+  __nv_bfloat16* o_hi;
+  __nv_bfloat16* o_lo;
+  float* o_f32;
+  long long ldo;
+};
+struct AttnPlan {
+  AttnArgs args;
+  dim3 grid;
+  double flops;
+};
+int attn_plan_init(AttnPlan* plan, const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk,
+                   int nk_pad);
+int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo,
+                cudaStream_t st);
+
+// spatial memory (memory.cu)
+int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int Mpad, float scale, float thresh,
+                       __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st);
+int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long long ldP, int B, int nq, int M,
+                      float* mem_attn, long long ld_attn, cudaStream_t st);
+int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ldo,
+                           long long out_batch_stride, int col0, cudaStream_t st);
+int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stride, int B, int T, int P, int C,
+                     float* scratch, float* out, cudaStream_t st);
 
 // fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output
 int launch_attention(const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk, int nk_pad,

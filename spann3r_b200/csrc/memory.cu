@@ -1,0 +1,213 @@
+// Spatial-memory kernels (spann3r/model.py:97-118,145-183): the softmax / threshold / renormalise
+// stage between the two tensor-core GEMMs of the bank read, the attention column sums, the transposed
+// split-bf16 write of bank values, and the working-memory similarity gate.
+//
+// Bank layout in HBM: keys and values are stored PRE-NORMALISED (LN_k / LN_v applied once at
+// write time; LayerNorm is per token, so this equals normalising the whole bank on every read as the
+// reference does) as split-bf16 planes: K_n [B, Mcap, 1024] (GEMM B operand of S = Q K^T) and V_n^T
+// [B, 1024, Mcap] (K-major B operand of O = P V).  Both are streamed by TMA in 128-byte rows.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace s3r {
+
+// ------------------------------------------------------------------------------------------------
+// One CTA per query row.  S row (raw dot products) -> softmax(S*scale) -> zero entries < thresh ->
+// renormalise (spann3r/model.py:157-172) -> split-bf16 planes P[row, 0:Mpad] (zero padded).
+// A row whose every weight is below the threshold divides 0/0 exactly like the reference (NaN).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restrict__ S, long long ldS, int M, int Mpad,
+                                                          float scale, float thresh, __nv_bfloat16* __restrict__ phi,
+                                                          __nv_bfloat16* __restrict__ plo, long long ldP) {
+  extern __shared__ float row[];
+  __shared__ float red[8];
+  const long long r = blockIdx.x;
+  const float* s = S + r * ldS;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  auto block_reduce = [&](float v, bool is_max) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, t) : v + t;
+    }
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float x = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) x = is_max ? fmaxf(x, red[i]) : x + red[i];
+    return x;
+  };
+  float mx = -INFINITY;
+  for (int i = tid; i < M; i += 256) {
+    const float v = s[i] * scale;
+    row[i] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_reduce(mx, true);
+  float sum = 0.f;
+  for (int i = tid; i < M; i += 256) {
+    const float e = expf(row[i] - mx);
+    row[i] = e;
+    sum += e;
+  }
+  sum = block_reduce(sum, false);
+  const float inv = 1.0f / sum;
+  float sum2 = 0.f;
+  for (int i = tid; i < M; i += 256) {
+    float a = row[i] * inv;
+    if (thresh > 0.f && a < thresh) a = 0.f;
+    row[i] = a;
+    sum2 += a;
+  }
+  float inv2 = 1.0f;
+  if (thresh > 0.f) {
+    sum2 = block_reduce(sum2, false);
+    inv2 = 1.0f / sum2;  // 0/0 -> NaN when the whole row was cut, as in the reference
+  }
+  __nv_bfloat16* ph = phi + r * ldP;
+  __nv_bfloat16* pl = plo + r * ldP;
+  for (int i = tid; i < Mpad; i += 256) {
+    float a = 0.f;
+    if (i < M) a = (thresh > 0.f) ? row[i] * inv2 : row[i];
+    __nv_bfloat16 h, l;
+    split_bf16(a, h, l);
+    ph[i] = h;
+    pl[i] = l;
+  }
+}
+
+int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int Mpad, float scale, float thresh,
+                       __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st) {
+  if (rows == 0 || M == 0) return 0;
+  const size_t smem = (size_t)M * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("mem_softmax: bank of %d tokens exceeds the 51200-token row buffer", M);
+    return -1;
+  }
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(mem_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = 200 * 1024;
+  }
+  mem_softmax_kernel<<<(unsigned)rows, 256, smem, st>>>(S, ldS, M, Mpad, scale, thresh, phi, plo, ldP);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mem_attn[b, m] += sum over the N query rows of attn[b, :, m]   (spann3r/model.py:180-181).
+// One thread per bank column, fixed summation order (deterministic: the prune ranking depends on it).
+// ------------------------------------------------------------------------------------------------
+__global__ void mem_colsum_kernel(const __nv_bfloat16* __restrict__ phi, const __nv_bfloat16* __restrict__ plo,
+                                  long long ldP, int nq, int M, float* __restrict__ mem_attn, long long ld_attn) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (m >= M) return;
+  const __nv_bfloat16* ph = phi + (long long)b * nq * ldP + m;
+  const __nv_bfloat16* pl = plo + (long long)b * nq * ldP + m;
+  float acc = 0.f;
+  for (int r = 0; r < nq; ++r) acc += __bfloat162float(ph[r * ldP]) + __bfloat162float(pl[r * ldP]);
+  mem_attn[b * ld_attn + m] += acc;
+}
+
+int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long long ldP, int B, int nq, int M,
+                      float* mem_attn, long long ld_attn, cudaStream_t st) {
+  if (M == 0) return 0;
+  dim3 grid((M + 127) / 128, B);
+  mem_colsum_kernel<<<grid, 128, 0, st>>>(phi, plo, ldP, nq, M, mem_attn, ld_attn);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 x[b, t, c] (t < T, c < C)  ->  split-bf16 planes out[b, c, col0 + t] (row stride ldo): the
+// transposed write that appends normalised values to the V_n^T bank.  32x32 smem tile transpose.
+// ------------------------------------------------------------------------------------------------
+__global__ void split_transpose_kernel(const float* __restrict__ x, int T, int C, __nv_bfloat16* __restrict__ ohi,
+                                       __nv_bfloat16* __restrict__ olo, long long ldo, long long out_batch_stride,
+                                       int col0) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xb = x + (long long)b * T * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < C) ? xb[(long long)t * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[threadIdx.x][i], h, l);
+      const long long o = (long long)b * out_batch_stride + (long long)c * ldo + col0 + t;
+      ohi[o] = h;
+      olo[o] = l;
+    }
+  }
+}
+
+int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ldo,
+                           long long out_batch_stride, int col0, cudaStream_t st) {
+  if (B * T * C == 0) return 0;
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  split_transpose_kernel<<<grid, block, 0, st>>>(x, T, C, ohi, olo, ldo, out_batch_stride, col0);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Similarity gate (spann3r/model.py:97-118): out[b, t] = mean_p cos(feat_k[b,p,:], wm[b,t,p,:]) for the
+// last `wm` frames of the raw key bank.  One warp per (b, t, p); per-(b,t) sums are reduced in a fixed
+// order by a second tiny kernel so the > 0.95 decision is reproducible.
+// ------------------------------------------------------------------------------------------------
+__global__ void cos_rows_kernel(const float* __restrict__ feat, const float* __restrict__ wm, long long wm_batch_stride,
+                                int B, int T, int P, int C, float* __restrict__ cosv) {
+  const long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)B * T * P;
+  if (w >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int p = (int)(w % P);
+  const int t = (int)((w / P) % T);
+  const int b = (int)(w / ((long long)P * T));
+  const float4* a = reinterpret_cast<const float4*>(feat + ((long long)b * P + p) * C);
+  const float4* k = reinterpret_cast<const float4*>(wm + (long long)b * wm_batch_stride + ((long long)t * P + p) * C);
+  float dot = 0.f, na = 0.f, nk = 0.f;
+  for (int i = lane; i < C / 4; i += 32) {
+    const float4 x = a[i], y = k[i];
+    dot += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    na += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    nk += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    na += __shfl_xor_sync(0xffffffffu, na, o);
+    nk += __shfl_xor_sync(0xffffffffu, nk, o);
+  }
+  if (lane == 0) cosv[w] = dot / (fmaxf(sqrtf(na), 1e-12f) * fmaxf(sqrtf(nk), 1e-12f));  // F.normalize eps
+}
+
+__global__ void mean_rows_kernel(const float* __restrict__ cosv, int P, float* __restrict__ out) {
+  __shared__ float red[256];
+  const float* c = cosv + (long long)blockIdx.x * P;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < P; i += 256) s += c[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = red[0] / (float)P;
+}
+
+int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stride, int B, int T, int P, int C,
+                     float* scratch, float* out, cudaStream_t st) {
+  if (B * T * P == 0) return 0;
+  if (C % 4) { set_error("check_sim: C %% 4 != 0"); return -1; }
+  const long long total = (long long)B * T * P;
+  cos_rows_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(feat, wm, wm_batch_stride, B, T, P, C, scratch);
+  mean_rows_kernel<<<B * T, 256, 0, st>>>(scratch, P, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+}  // namespace s3r

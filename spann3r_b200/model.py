@@ -1,0 +1,342 @@
+"""Drop-in `Spann3R` / `SpatialMemory` / DUSt3R module for the reference's callers.
+
+Mirrors the reference's public surface (spann3r/model.py:11-226,473-539; dust3r/model.py:84-225) --
+same class names, constructor signature, `state_dict` keys (1101, strict-loadable both ways), the
+`.dust3r` attribute, `forward(frames, return_memory=False) -> (preds, preds_all[, sp_mem])` with the
+same dict keys / shapes -- so `demo.py` / `eval.py` run by changing one import.
+
+The modules below hold parameters only.  All arithmetic runs in libspann3r_b200.so through
+`engine.Engine`; there is no eager-PyTorch, CPU or Triton path -- on a machine without an sm_100
+GPU `forward` raises.  Inference (eval mode) only: the training-mode branches of the reference
+(memory dropout, attn_thresh=0, autograd) are out of scope this round.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import torch
+import torch.nn as nn
+
+from . import synth
+from .engine import Engine, MemoryBank, PackedWeights
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter tree with the reference's exact key layout
+# ------------------------------------------------------------------------------------------------
+class ParamModule(nn.Module):
+    """A container of parameters / sub-containers (no forward: compute lives in the CUDA library)."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("spann3r_b200 leaf modules hold parameters only; call Spann3R.forward / the .dust3r "
+                           "stage methods (the fused CUDA path) instead")
+
+
+def build_param_tree(root: nn.Module, keys_shapes: dict, prefix: str = ""):
+    """Create nested ParamModules under `root` so that root.state_dict() has exactly the given keys, in order.
+    Aliased keys (dpt scratch.layerK_rn == scratch.layer_rn.K-1) share one Parameter, as in the reference."""
+    shared = {}
+    for key, shape in keys_shapes.items():
+        if not key.startswith(prefix):
+            continue
+        parts = key[len(prefix):].split(".")
+        mod = root
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, ParamModule())
+            mod = mod._modules[p]
+        canon = synth.canonical_key(key)
+        if canon not in shared:
+            shared[canon] = nn.Parameter(torch.empty(tuple(shape), dtype=torch.float32), requires_grad=False)
+        mod.register_parameter(parts[-1], shared[canon])
+    return root
+
+
+class AsymmetricCroCo3DStereo(ParamModule):
+    """Parameter holder + stage methods of dust3r/model.py:53-225 (ViT-L encoder, twin ViT-B decoder, DPT heads)."""
+
+    enc_embed_dim, dec_embed_dim, enc_depth, dec_depth = 1024, 768, 24, 12
+
+    def __init__(self, spec=None):
+        super().__init__()
+        spec = spec or synth.load_spec()
+        build_param_tree(self, spec["spann3r"], prefix="dust3r.")
+        self._owner = None  # set by Spann3R
+
+    def load_state_dict(self, ckpt, strict=True, **kw):
+        # dust3r/model.py:94-101: a checkpoint without dec_blocks2 duplicates dec_blocks into it
+        new = dict(ckpt)
+        if not any(k.startswith("dec_blocks2") for k in ckpt):
+            for k, v in ckpt.items():
+                if k.startswith("dec_blocks"):
+                    new[k.replace("dec_blocks", "dec_blocks2")] = v
+        return super().load_state_dict(new, strict=strict, **kw)
+
+    # -- stage methods, same names / argument meaning as the reference -------------------------------
+    def _encode_image(self, image, true_shape=None):
+        """dust3r/model.py:131-154 -> (x [B,N,1024], pos [B,N,2] int64, None)."""
+        eng = self._owner._engine_for(image.shape[0], image.shape[-2], image.shape[-1], encode_only=True)
+        x = eng.encode(self._owner._dev(image))
+        return x, self._owner._positions(image.shape[0], image.shape[-2], image.shape[-1]), None
+
+    def _decoder(self, f1, pos1, f2, pos2):
+        """dust3r/model.py:186-205 -> (dec1, dec2), 13 tensors each ([f_enc, d1..d12], d12 normed)."""
+        o = self._owner
+        eng = o._engine_for(f1.shape[0], o._hw[0], o._hw[1])
+        dec_all = eng.decode(f1.contiguous(), f2.contiguous(), want_all=True)
+        dec1 = [f1] + [dec_all[l, 0] for l in range(12)]
+        dec2 = [f2] + [dec_all[l, 1] for l in range(12)]
+        o._last_dec = (id(dec1[-1]), id(dec2[-1]))
+        return dec1, dec2
+
+    def forward(self, view1, view2):
+        """Pairwise DUSt3R forward (dust3r/model.py:213-225) for `dust3r.inference.inference`."""
+        o = self._owner
+        img1, img2 = o._dev(view1["img"]), o._dev(view2["img"])
+        B, _, H, W = img1.shape
+        eng = o._engine_for(B, H, W)
+        feats = eng.encode(torch.cat((img1, img2), dim=0).contiguous())
+        eng.decode(feats[:B].contiguous(), feats[B:].contiguous())
+        pts, conf = eng.heads()
+        return ({"pts3d": pts[0], "conf": conf[0]}, {"pts3d_in_other_view": pts[1], "conf": conf[1]})
+
+
+# ------------------------------------------------------------------------------------------------
+# spatial memory
+# ------------------------------------------------------------------------------------------------
+class SpatialMemory:
+    """spann3r/model.py:11-210 with the bank resident in pre-allocated device buffers (engine.MemoryBank).
+
+    Same attributes (`mem_k`, `mem_v`, `mem_attn`, `mem_count`, `wm`, `lm`, `num_patches`) and methods
+    (`add_mem`, `add_mem_check`, `check_sim`, `memory_read`, `memory_prune`) as the reference class;
+    `norm_q/k/v` are applied inside the CUDA library (LN_k / LN_v once at write time)."""
+
+    def __init__(self, norm_q=None, norm_k=None, norm_v=None, mem_dropout=None, long_mem_size=4000, work_mem_size=5,
+                 attn_thresh=5e-4, sim_thresh=0.95, save_attn=False, num_patches=None, *, engine: Engine = None):
+        if engine is None:
+            raise RuntimeError("SpatialMemory needs the CUDA engine (no CPU path)")
+        if mem_dropout is not None and getattr(mem_dropout, "training", False):
+            raise NotImplementedError("training-mode memory dropout is not implemented (inference path only)")
+        self.engine = engine
+        self.attn_thresh = attn_thresh
+        self.long_mem_size = long_mem_size
+        self.work_mem_size = work_mem_size
+        self.top_k = long_mem_size
+        self.sim_thresh = sim_thresh
+        self.num_patches = num_patches
+        self.bank = None
+        self.init_mem()
+
+    def init_mem(self):
+        self.lm = 0
+        self.wm = 0
+        if self.bank is not None:
+            self.bank.len = 0
+
+    def _ensure_bank(self, P):
+        if self.bank is None:
+            cap = self.long_mem_size + (self.work_mem_size + 3) * P
+            self.bank = MemoryBank(self.engine.B, cap, self.engine.device)
+
+    # reference-compatible views
+    @property
+    def mem_k(self):
+        return None if self.bank is None or self.bank.len == 0 else self.bank.k_raw[:, : self.bank.len]
+
+    @property
+    def mem_v(self):
+        return None if self.bank is None or self.bank.len == 0 else self.bank.v_raw[:, : self.bank.len]
+
+    @property
+    def mem_attn(self):
+        return None if self.bank is None or self.bank.len == 0 else self.bank.attn[:, : self.bank.len, None]
+
+    @property
+    def mem_count(self):
+        return None if self.bank is None or self.bank.len == 0 else self.bank.count[:, : self.bank.len, None]
+
+    def add_mem(self, feat_k, feat_v, pts_cur=None, img_cur=None):  # :80-95
+        if self.num_patches is None:
+            self.num_patches = feat_k.shape[1]
+        self._ensure_bank(self.num_patches)
+        self.engine.memory_append(self.bank, feat_k, feat_v)
+
+    def check_sim(self, feat_k, thresh=0.7):  # :97-118
+        if self.bank is None or self.bank.len == 0 or thresh == 1.0:
+            return False
+        mean_corr = self.engine.check_sim(self.bank, feat_k, self.wm)
+        mx = float(mean_corr.max())            # host sync, as in the reference (:114)
+        if mx > thresh:
+            print("Similarity detected:", mx)
+            return True
+        return False
+
+    def add_mem_check(self, feat_k, feat_v, pts_cur=None, img_cur=None):  # :120-143
+        if self.num_patches is None:
+            self.num_patches = feat_k.shape[1]
+        if self.check_sim(feat_k, thresh=self.sim_thresh):
+            return
+        self.add_mem(feat_k, feat_v, pts_cur, img_cur)
+        self.wm += 1
+        if self.wm > self.work_mem_size:
+            self.wm -= 1
+            if self.long_mem_size == 0:
+                P = self.num_patches
+                idx = torch.arange(P, self.bank.len, device=self.engine.device)[None].expand(self.bank.batch, -1)
+                self.bank.gather(idx.contiguous())
+            else:
+                self.lm += self.num_patches
+        if self.lm > self.long_mem_size:
+            self.memory_prune()
+            self.lm = self.top_k - self.wm * self.num_patches
+
+    def memory_read(self, feat, res=True):  # :145-183
+        if not res:
+            raise NotImplementedError("memory_read(res=False) is never used by the reference")
+        return self.engine.memory_read(self.bank, feat, self.attn_thresh)
+
+    def memory_prune(self):  # :185-210 -- selection stays torch.topk on identical inputs
+        n = self.bank.len
+        weights = self.bank.attn[:, :n] / self.bank.count[:, :n]
+        weights[self.bank.count[:, :n] < self.work_mem_size + 5] = 1e8
+        _, idx = torch.topk(weights, self.top_k, dim=1)
+        self.bank.gather(idx)
+        print("Memory pruned:", n, "->", self.bank.len)
+
+
+# ------------------------------------------------------------------------------------------------
+# Spann3R
+# ------------------------------------------------------------------------------------------------
+class Spann3R(ParamModule):
+    def __init__(self, dus3r_name="./checkpoints/DUSt3R_ViTLarge_BaseDecoder_512_dpt.pth", use_feat=False,
+                 mem_pos_enc=False, memory_dropout=0.15, max_encode_batch: int = 16):
+        super().__init__()
+        if use_feat or mem_pos_enc:
+            raise NotImplementedError("use_feat=True / mem_pos_enc=True variants are not built (the released "
+                                      "checkpoints and demo.py/eval.py use the defaults)")
+        self.use_feat, self.mem_pos_enc = use_feat, mem_pos_enc
+        spec = synth.load_spec()
+        self.dust3r = AsymmetricCroCo3DStereo(spec)
+        object.__setattr__(self.dust3r, "_owner", self)
+        rest = {k: v for k, v in spec["spann3r"].items() if not k.startswith("dust3r.")}
+        build_param_tree(self, rest)
+        self.memory_dropout = memory_dropout
+        self.max_encode_batch = max_encode_batch
+        self._packed = None
+        self._packed_version = None
+        self._engines = {}
+        self._pos_cache = {}
+        self._hw = None
+        if dus3r_name is not None:
+            self._load_dust3r(dus3r_name)
+
+    # -- checkpoint plumbing -----------------------------------------------------------------------
+    def _load_dust3r(self, path):
+        """dust3r/model.py:27-51 load_model: {'args': Namespace(model=...), 'model': state_dict}, strict=False."""
+        if not os.path.isfile(path):
+            raise FileNotFoundError(path)
+        torch.serialization.add_safe_globals([argparse.Namespace])
+        ckpt = torch.load(path, map_location="cpu")
+        args = ckpt["args"].model if "args" in ckpt else synth.DUST3R_ARGS
+        flat = args.replace(" ", "")
+        for need in ("enc_embed_dim=1024", "enc_depth=24", "dec_embed_dim=768", "dec_depth=12", "head_type='dpt'"):
+            if need not in flat:
+                raise ValueError(f"unsupported DUSt3R architecture (need {need}): {args}")
+        print("... loading model from", path)
+        print(self.dust3r.load_state_dict(ckpt["model"], strict=False))
+        # spann3r/model.py:240-241: pos_patch_embed starts as a copy of dust3r.patch_embed
+        self.pos_patch_embed.proj.weight.data.copy_(self.dust3r.patch_embed.proj.weight.data)
+        self.pos_patch_embed.proj.bias.data.copy_(self.dust3r.patch_embed.proj.bias.data)
+
+    def _version(self):
+        return tuple(p._version for p in self.parameters()) + (str(next(self.parameters()).device),)
+
+    def _weights(self) -> PackedWeights:
+        v = self._version()
+        if self._packed is None or v != self._packed_version:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("spann3r_b200.Spann3R runs on a B200 only: call .to('cuda') first (no CPU path)")
+            self._engines.clear()
+            self._packed = None
+            self._packed = PackedWeights(self.state_dict(), device=dev)
+            self._packed_version = v
+        return self._packed
+
+    def _engine_for(self, B, H, W, n_frames=2, encode_only=False) -> Engine:
+        w = self._weights()
+        self._hw = (H, W)
+        max_images = max(2 * B, min(n_frames * B, self.max_encode_batch * B))
+        key = (B, H, W)
+        eng = self._engines.get(key)
+        if eng is None or eng.max_images < max_images:
+            self._engines.pop(key, None)
+            eng = Engine(w, B, H, W, max_images=max_images)
+            self._engines[key] = eng
+        return eng
+
+    def _dev(self, t):
+        dev = next(self.parameters()).device
+        return t.to(dev, torch.float32, non_blocking=True).contiguous()
+
+    def _positions(self, B, H, W):
+        key = (H, W)
+        if key not in self._pos_cache:
+            dev = next(self.parameters()).device
+            y, x = torch.arange(H // 16, device=dev), torch.arange(W // 16, device=dev)
+            self._pos_cache[key] = torch.cartesian_prod(y, x)
+        return self._pos_cache[key].view(1, -1, 2).expand(B, -1, 2).clone()
+
+    # -- forward -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, frames, return_memory=False):
+        """spann3r/model.py:473-539 (eval mode)."""
+        if self.training:
+            raise NotImplementedError("spann3r_b200 implements the inference forward; call .eval() first")
+        F_ = len(frames)
+        img0 = frames[0]["img"]
+        B, _, H, W = img0.shape
+        if H > W:
+            raise NotImplementedError("portrait inputs (transpose_to_landscape, dust3r/utils/misc.py:66-94) not built")
+        eng = self._engine_for(B, H, W, n_frames=F_)
+        sp_mem = SpatialMemory(engine=eng)
+        N = eng.N
+
+        # The encoder has no dependence on the memory loop: encode every frame up front in large batches
+        # (SURVEY.md §3.1); per-image results are identical to the reference's pair / single-frame calls.
+        imgs = [self._dev(f["img"]) for f in frames]
+        feats = []
+        chunk = max(1, eng.max_images // B)
+        for s in range(0, F_, chunk):
+            part = imgs[s: s + chunk]
+            out = eng.encode(torch.cat(part, dim=0) if len(part) > 1 else part[0])
+            feats += list(out.view(len(part), B, N, 1024).unbind(0))
+
+        feat_k2 = None
+        preds, preds_all = None, []
+        for i in range(F_ - 1):
+            feat1, feat2 = feats[i], feats[i + 1]
+            feat_fuse = sp_mem.memory_read(feat_k2, res=True) if feat_k2 is not None else feat1
+            eng.decode(feat_fuse, feat2)
+            feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
+            pts, conf = eng.heads()
+            res1 = {"pts3d": pts[0], "conf": conf[0]}
+            res2 = {"pts3d": pts[1], "conf": conf[1]}
+            mem_v = eng.value(res1["pts3d"], feat_k1)            # encode_cur_value(...) + feat_k1
+            sp_mem.add_mem_check(feat_k1, mem_v)
+            res2["pts3d_in_other_view"] = res2.pop("pts3d")
+            if preds is None:
+                preds = [res1]
+                preds_all = [(res1, res2)]
+            else:
+                res1["pts3d_in_other_view"] = res1.pop("pts3d")
+                preds.append(res1)
+                preds_all.append((res1, res2))
+        preds.append(res2)
+        if return_memory:
+            return preds, preds_all, sp_mem
+        return preds, preds_all
+
+    def offline_reconstruction(self, frames, graph):
+        raise NotImplementedError("offline_reconstruction (spann3r/model.py:394-471) is a SURVEY.md §8f 'next' row")

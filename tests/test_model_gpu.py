@@ -1,0 +1,127 @@
+"""End-to-end parity of the CUDA path (`spann3r_b200.Spann3R.forward`, called through the C ABI) against
+(a) the committed golden vectors produced by the REAL reference on CPU in strict fp32, and
+(b) the pinned oracle, stage by stage.  Tolerance = BASELINE.json north_star: 1e-3 relative (L2) in fp32.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, get_state_dict, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def models():
+    from spann3r_b200 import Spann3R
+    out = {}
+    for sharpen in (False, True):
+        m = Spann3R(dus3r_name=None)
+        m.load_state_dict(get_state_dict(sharpen), strict=True)
+        out[sharpen] = m.cuda().eval()
+    return out
+
+
+CASES = [
+    ("cfg1_224_2f_raw.npz", False, 2, 224, 224),
+    ("seq_224_4f_sharp.npz", True, 4, 224, 224),
+    ("seq_384x512_3f_sharp.npz", True, 3, 384, 512),
+]
+
+
+@pytest.mark.parametrize("fname,sharpen,nf,H,W", CASES)
+def test_forward_matches_reference_golden(models, fname, sharpen, nf, H, W):
+    from spann3r_b200 import synth
+    g = np.load(os.path.join(GOLDEN, fname))
+    frames = synth.make_frames(nf, H, W)
+    preds, preds_all, mem = models[sharpen](frames, return_memory=True)
+    torch.cuda.synchronize()
+    s = int(g["meta/px_stride"])
+    errs = {}
+    for i, p in enumerate(preds):
+        assert set(p.keys()) == {k.split("/")[-1] for k in g.files if k.startswith(f"preds/{i}/")}
+        for k, v in p.items():
+            errs[f"preds/{i}/{k}"] = rel_l2(v[:, ::s, ::s].cpu(), g[f"preds/{i}/{k}"])
+    for i, (_, r2) in enumerate(preds_all):
+        for k, v in r2.items():
+            errs[f"preds_all/{i}/res2/{k}"] = rel_l2(v[:, ::s, ::s].cpu(), g[f"preds_all/{i}/res2/{k}"])
+    errs["mem_k"] = rel_l2(mem.mem_k[:, ::7, ::8].cpu(), g["mem/mem_k_sub"])
+    errs["mem_v"] = rel_l2(mem.mem_v[:, ::7, ::8].cpu(), g["mem/mem_v_sub"])
+    errs["mem_attn"] = rel_l2(mem.mem_attn.cpu(), g["mem/mem_attn"])
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert np.array_equal(mem.mem_count.cpu().numpy(), g["mem/mem_count"])
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+def test_stagewise_vs_oracle(models):
+    """Each engine stage against the oracle evaluated on the GPU in strict fp32 (no TF32)."""
+    from oracle import spann3r_oracle as orc
+    from spann3r_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = models[True]
+    sd = {k: v.cuda() for k, v in get_state_dict(True).items()}
+    H, W, B = 224, 224, 1
+    frames = synth.make_frames(2, H, W)
+    img = torch.cat([f["img"] for f in frames]).cuda()
+    eng = m._engine_for(B, H, W)
+    feats = eng.encode(img)
+    ref_feats, pos = orc.encode_image(sd, img)
+    assert rel_l2(feats.cpu(), ref_feats.cpu()) < 2e-4
+    f1, f2 = ref_feats[:1].contiguous(), ref_feats[1:].contiguous()
+    dec_all = eng.decode(f1, f2, want_all=True)
+    rdec1, rdec2 = orc.decoder(sd, f1, pos[:1], f2, pos[1:])
+    for l in (0, 5, 11):
+        assert rel_l2(dec_all[l, 0].cpu(), rdec1[l + 1].cpu()) < 2e-4, l
+        assert rel_l2(dec_all[l, 1].cpu(), rdec2[l + 1].cpu()) < 2e-4, l
+    k1, k2 = eng.keyheads(f1, f2)
+    assert rel_l2(k1.cpu(), orc.key_head(sd, 1, f1, rdec1[-1]).cpu()) < 2e-4
+    assert rel_l2(k2.cpu(), orc.key_head(sd, 2, f2, rdec2[-1]).cpu()) < 2e-4
+    pts, conf = eng.heads()
+    r1 = orc.dpt_head(sd, "dust3r.downstream_head1", rdec1, H, W)
+    r2 = orc.dpt_head(sd, "dust3r.downstream_head2", rdec2, H, W)
+    assert rel_l2(pts[0].cpu(), r1["pts3d"].cpu()) < 3e-4 and rel_l2(conf[0].cpu(), r1["conf"].cpu()) < 3e-4
+    assert rel_l2(pts[1].cpu(), r2["pts3d"].cpu()) < 3e-4 and rel_l2(conf[1].cpu(), r2["conf"].cpu()) < 3e-4
+    rk1 = orc.key_head(sd, 1, f1, rdec1[-1])
+    v = eng.value(r1["pts3d"].contiguous(), rk1.contiguous())
+    assert rel_l2(v.cpu(), (orc.encode_cur_value(sd, r1["pts3d"]) + rk1).cpu()) < 2e-4
+    # memory: append two frames, read, compare with the oracle's SpatialMemory
+    from spann3r_b200.model import SpatialMemory
+    sp = SpatialMemory(engine=eng)
+    om = orc.SpatialMemory(sd)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(2):
+        fk = torch.randn(1, eng.N, 1024, generator=g).cuda()
+        fv = torch.randn(1, eng.N, 1024, generator=g).cuda()
+        sp.add_mem_check(fk, fv)
+        om.add_mem_check(fk, fv)
+    q = torch.randn(1, eng.N, 1024, generator=g).cuda()
+    out = sp.memory_read(q)
+    ref = om.memory_read(q)
+    assert rel_l2(out.cpu(), ref.cpu()) < 2e-4
+    assert rel_l2(sp.mem_attn.cpu(), om.mem_attn.cpu()) < 2e-4
+    assert torch.equal(sp.mem_count.cpu(), om.mem_count.cpu())
+    assert sp.wm == om.wm == 2
+
+
+def test_batched_sequences_match_single(models):
+    """B = 2 sequences in lockstep == each sequence alone (BASELINE config 3 runs batches of sequences)."""
+    from spann3r_b200 import synth
+    m = models[True]
+    fa = synth.make_frames(3, 224, 224, seed0=1)
+    fb = synth.make_frames(3, 224, 224, seed0=101)
+    both = [{"img": torch.cat((a["img"], b["img"]))} for a, b in zip(fa, fb)]
+    pa, _ = m(fa)
+    pa = [{k: v.clone() for k, v in p.items()} for p in pa]
+    pb, _ = m(fb)
+    pb = [{k: v.clone() for k, v in p.items()} for p in pb]
+    pboth, _ = m(both)
+    for i in range(3):
+        for k in pa[i]:
+            assert rel_l2(pboth[i][k][0:1].cpu(), pa[i][k].cpu()) < 1e-5, (i, k)
+            assert rel_l2(pboth[i][k][1:2].cpu(), pb[i][k].cpu()) < 1e-5, (i, k)
