@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Benchmark of the Spann3R per-frame forward path (BASELINE.json metric: frames/sec, 10-frame 512x384
+sequence through encoder -> memory-attn -> decoder -> DPT).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+One "step" = one whole 10-frame 512x384 sequence (BASELINE config[1]) through `Spann3R.forward` (eval mode,
+batch 1 per GPU, spatial memory reset per sequence).  N > 1: one process per GPU (torchrun), every rank runs its
+own independent sequences (weak scaling, no data-path collective -- SURVEY.md §8e); time = max over ranks.
+Rank 0 prints ONE JSON line.  Keys beyond the base contract: `roofline` (dominant kernel = the split-bf16
+tcgen05 GEMM/conv engine, CUDA-event timed per launch in a separate profiling pass), `cpu_baseline` (the oracle
+port of the reference on the host cores, bounded sample), `e2e` (same metric with pinned-host inputs copied H2D
+and predictions copied D2H inside the timed region), `gpu_launches`, `clocks`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES, HEIGHT, WIDTH = 10, 384, 512
+FLOP_PER_SEQ = 13.95e12            # algorithmic, SURVEY.md §8a (10 frames, B=1, 512x384)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=float(d.get("bf16_tflops_sustained", 1454.1)), hbm=float(d.get("hbm_gbs", 6578.3)),
+                    src="measured (MEASURED_PEAKS.json, bf16 sustained)")
+    return dict(bf16_sustained=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference's own algorithm on the host cores (the oracle port, pinned to the real reference by
+    tests/test_oracle_vs_golden.py).  Each step = a bounded sample of the workload: a 3-frame 512x384 sequence."""
+    rank, world, _ = _dist()
+    if rank != 0:
+        return
+    from oracle import spann3r_oracle as orc
+    from spann3r_b200 import synth
+    nf = 3
+    sd = synth.make_state_dict(sharpen=True)
+    frames = synth.make_frames(nf, HEIGHT, WIDTH)
+    cores = torch.get_num_threads()
+    for _ in range(min(args.warmup, 1)):
+        orc.forward(sd, frames)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.time()
+    for _ in range(steps):
+        orc.forward(sd, frames)
+    dt = (time.time() - t0) / steps
+    fps = nf / dt
+    sample = f"{nf}-frame {WIDTH}x{HEIGHT} sequence per step, {steps} steps, torch CPU fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "frames/sec (512x384, 10-frame seq) enc->mem-attn->dec->DPT", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bounded sample: {nf}-frame {WIDTH}x{HEIGHT} sequence, batch 1, random-init sharpened ckpt"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = _dist()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from spann3r_b200 import Spann3R, synth
+
+    W_ = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    F_ = args.frames
+    sd = synth.make_state_dict(sharpen=True)
+    model = Spann3R(dus3r_name=None)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+
+    # per-rank independent sequences (seeds differ per rank and per step)
+    def host_frames(step):
+        fr = synth.make_frames(F_, HEIGHT, WIDTH, seed0=1 + 1000 * rank + 100 * step)
+        return [{"img": f["img"].pin_memory()} for f in fr]
+
+    n_distinct = 2
+    host = [host_frames(s) for s in range(n_distinct)]
+    resident = [[{"img": f["img"].to(dev)} for f in seq] for seq in host]
+    out_host = None
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- warm-up (also builds every tensor map / plan) ----
+    for i in range(W_):
+        model(resident[i % n_distinct])
+    eng = model._engine_for(1, HEIGHT, WIDTH, n_frames=F_)
+    torch.cuda.synchronize(dev)
+
+    # ---- timed: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.take_launches(); eng.take_flops()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        model(resident[i % n_distinct])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.take_launches()
+    flops_issued = eng.take_flops()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * F_ * K / (ms / 1e3)
+
+    # ---- timed: end to end through the public API, pinned host inputs -> device, predictions -> pinned host ----
+    def e2e_step(seq_host):
+        nonlocal out_host
+        frames = [{"img": f["img"].to(dev, non_blocking=True)} for f in seq_host]
+        preds, _ = model(frames)
+        outs = [p[k] for p in preds for k in sorted(p)]
+        if out_host is None:
+            out_host = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
+        for o, h in zip(outs, out_host):
+            h.copy_(o, non_blocking=True)
+        return outs
+
+    e2e_step(host[0])
+    torch.cuda.synchronize(dev)
+    barrier()
+    e0.record()
+    for i in range(K):
+        outs = e2e_step(host[i % n_distinct])
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    h2d = F_ * 3 * HEIGHT * WIDTH * 4
+    d2h = sum(o.numel() * 4 for o in outs)
+    e2e = world * F_ * K / (ms_e2e / 1e3)
+
+    # ---- roofline leg: per-launch CUDA-event timing of the tensor-core kernels (separate, untimed pass) ----
+    eng.profile(True)
+    model(resident[0])
+    prof = eng.profile_read()
+    eng.profile(False)
+    pk = _peaks()
+    gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16x3_kernel (split-bf16 tcgen05 GEMM / implicit-GEMM conv)",
+        "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["bf16_sustained"],
+        "traffic": traffic, "peak_source": pk["src"],
+        "note": "achieved = algorithmic 2MNK FLOPs / CUDA-event time summed over all GEMM/conv launches of one sequence; "
+                "the split-bf16 scheme issues 3 MMAs per product, so issued-MMA rate = 3x achieved (cap 1/3 of peak)",
+        "gemm_launches_per_seq": prof["gemm_launches"], "gemm_ms_per_seq": prof["gemm_ms"],
+        "gemm_flops_per_launch": prof["gemm_flops"] / max(prof["gemm_launches"], 1),
+        "attention_ms_per_seq": prof["attn_ms"], "attention_tflops": (prof["attn_flops"] / (prof["attn_ms"] * 1e-3) / 1e12
+                                                                       if prof["attn_ms"] > 0 else 0.0),
+        "whole_path_frac": (FLOP_PER_SEQ * F_ / FRAMES * K * world / (ms / 1e3)) / 1e12 / pk["bf16_sustained"] / world,
+    }
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import spann3r_oracle as orc
+        nf = 3
+        frames = synth.make_frames(nf, HEIGHT, WIDTH)
+        t0 = time.time()
+        orc.forward(sd, frames)
+        dt = time.time() - t0
+        cpu = {"value": nf / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"one {nf}-frame {WIDTH}x{HEIGHT} sequence, oracle port (torch CPU fp32), {dt:.1f}s"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "frames/sec (512x384, 10-frame seq) enc->mem-attn->dec->DPT", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; tf32 attention)", "data": "synthetic",
+            "config": {"workload": f"{F_}-frame {WIDTH}x{HEIGHT} sequence per step, batch 1 per GPU, ViT-L enc / ViT-B dec + DPT, "
+                                   "random-init sharpened checkpoint (SURVEY.md §8d config 2)",
+                       "parallelism": f"{world} independent replicas (one sequence stream per GPU, no collective)",
+                       "l2": "per-step working set (2.6 GB packed weights + activations) >> 126 MB L2; inputs alternate between "
+                             "2 distinct sequences"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches, "issued_algorithmic_tflop_per_step": flops_issued / K / 1e12,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,10 @@ int s3r_engine_memory_append(s3r_engine* e, const s3r_bank* bank, const float* f
 int s3r_engine_check_sim(s3r_engine* e, const s3r_bank* bank, const float* feat_k, int wm, float* out, void* stream);
 /* algorithmic FLOPs (2*M*N*K of every tensor-core launch) issued since the last call; resets the counter */
 double s3r_engine_take_flops(s3r_engine* e);
+/* Per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline leg): switch on, run, read.
+ * profile_read synchronises the device; out = {gemm_ms, gemm_flops, gemm_launches, attn_ms, attn_flops, attn_launches} */
+void s3r_engine_profile(s3r_engine* e, int on);
+int s3r_engine_profile_read(s3r_engine* e, double* out);
 /* number of kernel launches since the last call; resets the counter */
 long long s3r_engine_take_launches(s3r_engine* e);
 

@@ -68,6 +68,15 @@ struct s3r_engine {
   double flops = 0;
   long long launches = 0;
   int status = 0;
+  // optional per-launch timing of the tensor-core kernels (bench.py roofline leg)
+  bool profiling = false;
+  struct Timed { cudaEvent_t a, b; double flops; int kind; };   // kind 0 = GEMM/conv, 1 = attention
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
 
   // lookup tables
   int* pos = nullptr;  // [max_rows, 2] (y, x)
@@ -136,7 +145,13 @@ struct s3r_engine {
     }
     flops += p.flops;
     ++launches;
-    return gemm_launch(p, st);
+    if (!profiling) return gemm_launch(p, st);
+    Timed t; t.a = get_event(); t.b = get_event(); t.flops = p.flops; t.kind = 0;
+    cudaEventRecord(t.a, st);
+    int r = gemm_launch(p, st);
+    cudaEventRecord(t.b, st);
+    timed.push_back(t);
+    return r;
   }
 
   int attention(PlanCache& pc, const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk,
@@ -153,7 +168,13 @@ struct s3r_engine {
     AttnPlan& p = pc.attns[pc.ac++];
     flops += p.flops;
     ++launches;
-    return attn_launch(p, out.hi, out.lo, nullptr, ldo, st);
+    if (!profiling) return attn_launch(p, out.hi, out.lo, nullptr, ldo, st);
+    Timed t; t.a = get_event(); t.b = get_event(); t.flops = p.flops; t.kind = 1;
+    cudaEventRecord(t.a, st);
+    int r = attn_launch(p, out.hi, out.lo, nullptr, ldo, st);
+    cudaEventRecord(t.b, st);
+    timed.push_back(t);
+    return r;
   }
 
   int ln(const float* x, const s3r_ln& w, long long wb_stride, long long rows_per_group, float eps, long long rows, int C,
@@ -321,6 +342,30 @@ double s3r_engine_take_flops(s3r_engine* e) {
   e->flops = 0;
   return f;
 }
+void s3r_engine_profile(s3r_engine* e, int on) { e->profiling = on != 0; }
+
+// Synchronises, then sums CUDA-event durations of the launches recorded while profiling was on.
+// out[0..3] = {gemm_ms, gemm_flops, gemm_launches, attn_ms}, out[4..5] = {attn_flops, attn_launches}
+int s3r_engine_profile_read(s3r_engine* e, double* out) {
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("profile_read: %s", cudaGetErrorString(cudaGetLastError()));
+    return -6;
+  }
+  for (auto& t : e->timed) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    const int o = t.kind == 0 ? 0 : 3;
+    out[o] += ms;
+    out[o + 1] += t.flops;
+    out[o + 2] += 1;
+    e->ev_pool.push_back(t.a);
+    e->ev_pool.push_back(t.b);
+  }
+  e->timed.clear();
+  return 0;
+}
+
 long long s3r_engine_take_launches(s3r_engine* e) {
   const long long n = e->launches;
   e->launches = 0;

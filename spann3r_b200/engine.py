@@ -81,6 +81,8 @@ _lib.register_protos({
     "s3r_engine_check_sim": (_i, [_vp, C.POINTER(Bank), _vp, _i, _vp, _vp]),
     "s3r_engine_take_flops": (C.c_double, [_vp]),
     "s3r_engine_take_launches": (C.c_longlong, [_vp]),
+    "s3r_engine_profile": (None, [_vp, _i]),
+    "s3r_engine_profile_read": (_i, [_vp, C.POINTER(C.c_double)]),
 })
 
 ROPE_MAXPOS = 64
@@ -354,6 +356,15 @@ class Engine:
 
     def take_flops(self) -> float:
         return float(_lib.lib().s3r_engine_take_flops(self._h))
+
+    def profile(self, on: bool):
+        _lib.lib().s3r_engine_profile(self._h, int(on))
+
+    def profile_read(self) -> dict:
+        out = (C.c_double * 6)()
+        _lib.check(_lib.lib().s3r_engine_profile_read(self._h, out), "profile_read")
+        return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), attn_ms=out[3], attn_flops=out[4],
+                    attn_launches=int(out[5]))
 
     def take_launches(self) -> int:
         return int(_lib.lib().s3r_engine_take_launches(self._h))
