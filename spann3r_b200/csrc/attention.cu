@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -312,8 +314,7 @@ int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, 
   }
   AttnArgs a = plan.args;
   a.o_hi = o_hi; a.o_lo = o_lo; a.o_f32 = o_f32; a.ldo = ldo;
-  attention_kernel<<<plan.grid, kThreads, SMEM, st>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(attention_kernel, plan.grid, dim3(kThreads), SMEM, st, a);
   if (e != cudaSuccess) {
     set_error("attention launch failed: %s", cudaGetErrorString(e));
     return -6;

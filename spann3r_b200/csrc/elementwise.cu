@@ -15,6 +15,8 @@ namespace s3r {
 __global__ void split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
                              __nv_bfloat16* __restrict__ lo, long long ldp, int col0, long long rows, int C,
                              int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4 = C >> 2;
   const long long total = rows * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -40,7 +42,7 @@ int launch_split(const float* x, long long ldx, __nv_bfloat16* hi, __nv_bfloat16
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  split_kernel<<<blocks, 256, 0, st>>>(x, ldx, hi, lo, ldp, col0, rows, C, relu);
+  launch_pdl(split_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, hi, lo, ldp, col0, rows, C, relu);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -58,6 +60,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
                                  float eps, long long rows, float* __restrict__ out, long long ldo,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp,
                                  int col0, long long swap_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int C = NV * 128;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -117,7 +121,7 @@ int launch_layernorm(const float* x, long long ldx, const float* w, const float*
   dim3 grid((unsigned)((rows + wpb - 1) / wpb)), block(wpb * 32);
 #define LN_CASE(NV)                                                                                            \
   case NV * 128:                                                                                               \
-    layernorm_kernel<NV><<<grid, block, 0, st>>>(x, ldx, w, b, wb_group_stride, rows_per_group, eps, rows, out, \
+    launch_pdl(layernorm_kernel<NV>, dim3(grid), dim3(block), 0, st, x, ldx, w, b, wb_group_stride, rows_per_group, eps, rows, out, \
                                                  ldo, hi, lo, ldp, col0, swap_rows);                           \
     break;
   switch (C) {
@@ -139,6 +143,8 @@ int launch_layernorm(const float* x, long long ldx, const float* w, const float*
 __global__ void im2col_patch16_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy,
                                       long long sx, int B, int gh, int gw, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * gh * gw * 48;  // (token, c, i): 16 consecutive j each
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -174,7 +180,7 @@ int launch_im2col_patch16(const float* img, long long sb, long long sc, long lon
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_patch16_kernel<<<blocks, 256, 0, st>>>(img, sb, sc, sy, sx, B, gh, gw, hi, lo);
+  launch_pdl(im2col_patch16_kernel, dim3(blocks), dim3(256), 0, st, img, sb, sc, sy, sx, B, gh, gw, hi, lo);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -185,6 +191,8 @@ int launch_im2col_patch16(const float* img, long long sb, long long sc, long lon
 __global__ void im2col_3x3s2_kernel(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo,
                                     int NB, int H, int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ ohi,
                                     __nv_bfloat16* __restrict__ olo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c8 = C >> 3;
   const long long total = (long long)NB * Ho * Wo * 9 * c8;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -215,7 +223,7 @@ int launch_im2col_3x3s2(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, int 
   if (total == 0) return 0;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_3x3s2_kernel<<<blocks, 256, 0, st>>>(ihi, ilo, NB, H, W, C, Ho, Wo, ohi, olo);
+  launch_pdl(im2col_3x3s2_kernel, dim3(blocks), dim3(256), 0, st, ihi, ilo, NB, H, W, C, Ho, Wo, ohi, olo);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -226,6 +234,8 @@ int launch_im2col_3x3s2(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const float* __restrict__ x, int NB, int H, int W, int C, float* __restrict__ out,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = 2 * H, Wo = 2 * W, c4 = C >> 2;
   const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
   const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
@@ -269,7 +279,7 @@ int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, _
   if (total == 0) return 0;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  upsample2x_kernel<<<(int)blocks, 256, 0, st>>>(x, NB, H, W, C, out, hi, lo);
+  launch_pdl(upsample2x_kernel, dim3((int)blocks), dim3(256), 0, st, x, NB, H, W, C, out, hi, lo);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -283,6 +293,8 @@ int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, _
 // ------------------------------------------------------------------------------------------------
 __global__ void rope2d_kernel(float* __restrict__ tokens, const long long* __restrict__ pos, long long BN, int H, int D,
                               long long stride_tok, long long stride_head, float base, float fwd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Q = D >> 2;
   const long long total = BN * H * 2 * Q;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -311,7 +323,7 @@ int launch_rope2d(float* tokens, const long long* pos, long long BN, int H, int 
   if (total == 0) return 0;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  rope2d_kernel<<<(int)blocks, 256, 0, st>>>(tokens, pos, BN, H, D, stride_tok, stride_head, base, fwd);
+  launch_pdl(rope2d_kernel, dim3((int)blocks), dim3(256), 0, st, tokens, pos, BN, H, D, stride_tok, stride_head, base, fwd);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

@@ -20,11 +20,13 @@
 //               ConvTranspose pixel shuffle / DPT head tail + postprocess.
 #include "gemm.cuh"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace s3r {
 
@@ -43,11 +45,6 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_GELU) return gelu_erf(v);
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  return v;
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmArgs args) {
@@ -90,6 +87,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -203,146 +202,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-        // bias
-        if (args.bias != nullptr) {
-          const int bcol = (args.epi == EPI_PIXSHUF) ? (col0 % args.ps_cout) : col0;
-          const int bstride = (args.epi == EPI_PIXSHUF) ? args.ps_cout : args.N;
-          const float4* bp = reinterpret_cast<const float4*>(args.bias + (long long)g * bstride + bcol);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 b = __ldg(bp + q);
-            v[4 * q + 0] += b.x;
-            v[4 * q + 1] += b.y;
-            v[4 * q + 2] += b.z;
-            v[4 * q + 3] += b.w;
-          }
-        }
-        if (args.act != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], args.act);
-        }
-
-        if (args.epi == EPI_PLAIN || args.epi == EPI_PIXSHUF) {
-          long long orow = grow;
-          int ocol = col0;
-          if (args.epi == EPI_PIXSHUF) {
-            const int ij = col0 / args.ps_cout;
-            ocol = col0 - ij * args.ps_cout;
-            const int s = args.ps_s;
-            const int i = ij / s, j = ij - i * s;
-            orow = (long long)g * args.out_group_rows +
-                   ((long long)nb * (args.H * s) + (h * s + i)) * (args.W * s) + (w * s + j);
-          }
-          if (valid) {
-            if (args.res1 != nullptr) {
-              const float4* rp = reinterpret_cast<const float4*>(args.res1 + orow * args.ldr1 + ocol);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 t = rp[q];
-                v[4 * q + 0] += t.x;
-                v[4 * q + 1] += t.y;
-                v[4 * q + 2] += t.z;
-                v[4 * q + 3] += t.w;
-              }
-            }
-            if (args.res2 != nullptr) {
-              const float4* rp = reinterpret_cast<const float4*>(args.res2 + orow * args.ldr2 + ocol);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 t = rp[q];
-                v[4 * q + 0] += t.x;
-                v[4 * q + 1] += t.y;
-                v[4 * q + 2] += t.z;
-                v[4 * q + 3] += t.w;
-              }
-            }
-            if (args.out_f32 != nullptr) {
-              float* op = args.out_f32 + orow * args.ldo + ocol;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) st_f4(op + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            if (args.out_hi != nullptr) {
-              uint32_t ph[16], pl[16];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                float a = v[2 * q], b = v[2 * q + 1];
-                if (args.plane_relu) {
-                  a = fmaxf(a, 0.f);
-                  b = fmaxf(b, 0.f);
-                }
-                __nv_bfloat16 ah, al, bh, bl;
-                split_bf16(a, ah, al);
-                split_bf16(b, bh, bl);
-                ph[q] = pack_bf16(ah, bh);
-                pl[q] = pack_bf16(al, bl);
-              }
-              const long long po = orow * args.ldp + args.plane_col0 + ocol;
-              uint4* hp = reinterpret_cast<uint4*>(args.out_hi + po);
-              uint4* lp = reinterpret_cast<uint4*>(args.out_lo + po);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                hp[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-                lp[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-              }
-            }
-          }
-        } else if (args.epi == EPI_QKV) {
-          // croco/models/blocks.py:97-104 (self) / :154-160 (cross) + RoPE2D (pos_embed.py:112-159,
-          // curope/kernels.cu:18-81): head dim 64 = [y half | x half], each half = 16 (u, v) pairs
-          // (j, j+16) rotated by pos * 100^(-j/16).
-          const int role = args.q_role_base + col0 / args.q_C;  // 0 q, 1 k, 2 v
-          const int cc = col0 % args.q_C;
-          const int head = cc >> 6;
-          const int d0 = cc & 63;  // 0 or 32
-          const int heads = args.q_C >> 6;
-          const int bidx = (int)(pix / args.q_ntok);
-          const int t = (int)(pix - (long long)bidx * args.q_ntok);
-          const long long gb = (long long)g * args.q_nb + bidx;
-          if (valid) {
-            if (role <= 1 && args.q_rope) {
-              const int p = args.q_pos[(grow) * 2 + (d0 >> 5)];
-              const float2* cs = args.q_cs + p * 16;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 t2 = __ldg(cs + j);
-                const float u = v[j], x = v[j + 16];
-                v[j] = u * t2.x - x * t2.y;
-                v[j + 16] = x * t2.x + u * t2.y;
-              }
-            }
-            if (role == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= args.q_scale;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = to_tf32(v[j]);
-            if (role <= 1) {
-              float* op = (role == 0 ? args.q_out : args.k_out) + ((gb * heads + head) * args.q_ntok + t) * 64 + d0;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) st_f4(op + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            } else {
-              float* op = args.vt_out + ((gb * heads + head) * 64 + d0) * (long long)args.q_ntok_pad + t;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) op[(long long)j * args.q_ntok_pad] = v[j];
-            }
-          }
-        } else {  // EPI_HEADTAIL: dpt_block.py:318-324 (ReLU, 1x1 conv) + heads/postprocess.py:10-58
-          const float* wt = args.ht_w + (long long)g * 4 * 128 + col0;
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const float4* wp = reinterpret_cast<const float4*>(wt + o * 128);
-            float acc = ht_acc[o];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t = __ldg(wp + q);
-              acc = fmaf(v[4 * q + 0], t.x, acc);
-              acc = fmaf(v[4 * q + 1], t.y, acc);
-              acc = fmaf(v[4 * q + 2], t.z, acc);
-              acc = fmaf(v[4 * q + 3], t.w, acc);
-            }
-            ht_acc[o] = acc;
-          }
-        }
+        epi_chunk(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
       }
       // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before_sync();
@@ -465,13 +325,32 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   a.tiles_w = (W + a.bw - 1) / a.bw;
   a.tiles_h = (H + a.bh - 1) / a.bh;
   a.out_group_rows = (long long)NB * H * W;
-  // tile width: keep >= ~1 wave of CTAs where the problem allows it
+  // Tile shape.  Measured on B200 (tools/gemm_sweep.py): the engine is bound by operand bytes
+  // through L2 -> SMEM, so prefer the 2-CTA kernel (256 x bn pair tiles: each SM stages only half of B) whenever the
+  // m-tile count is even; otherwise 1-CTA tiles as wide as still leaves ~3/4 of the SMs busy.
   const long long m_tiles = (long long)a.tiles_w * a.tiles_h * NB * groups;
-  int bn = 128;
+  const long long m_tiles_group = (long long)a.tiles_w * a.tiles_h * NB;
+  int bn = 128, two = 0;
   if (N >= 256 && m_tiles * ((N + 255) / 256) >= 2 * num_sms()) bn = 256;
-  else if (m_tiles * ((N + 127) / 128) < num_sms() && N >= 64) bn = 64;
+  else if (m_tiles * ((N + 127) / 128) < (3 * num_sms()) / 4 && N >= 64) bn = 64;
   if (N <= 64) bn = 64;
-  if (force_bn) bn = force_bn;
+  static const int g2_mode = getenv("S3R_GEMM2") ? atoi(getenv("S3R_GEMM2")) : 1;   // 0 off, 1 auto, 128/256 fixed
+  // 2-CTA pair tiles pay off once there are several waves of tiles (measured: +8..12% on the M=7680 encoder GEMMs,
+  // nothing at M=768 where fixed per-kernel costs dominate); g2_mode 128/256 forces them wherever they are legal.
+  const long long tiles128 = m_tiles * ((N + 127) / 128);
+  const bool legal2 = (m_tiles_group % 2 == 0) && N >= 128;
+  if (force_bn == 0 && legal2 && ((g2_mode == 1 && taps == 1 && tiles128 >= 400) || g2_mode == 128 || g2_mode == 256)) {
+    two = 1;
+    bn = (N >= 256 && N % 256 == 0) ? 256 : 128;
+    if (g2_mode == 128) bn = 128;
+  }
+  if (force_bn >= 2000) { two = 1; bn = force_bn - 2000; }
+  else if (force_bn > 0) { two = 0; bn = force_bn; }
+  if (two && (m_tiles_group % 2 != 0 || (bn != 128 && bn != 256))) {
+    set_error("gemm_plan_init: 2-CTA tiles need an even m-tile count per group and bn in {128,256}");
+    return -1;
+  }
+  plan->two_cta = two;
   plan->bn = bn;
 
   const uint64_t esz = 2;
@@ -487,7 +366,7 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
     uint64_t dims[3] = {(uint64_t)Kc, (uint64_t)taps, (uint64_t)(b_group_rows * (groups - 1) + N)};
     // with a single tap the tap stride is never used, but must still be a multiple of 16 bytes
     uint64_t str[2] = {(uint64_t)(taps == 1 ? ldb : Kc) * esz, (uint64_t)ldb * esz};
-    uint32_t box[3] = {(uint32_t)BK, 1, (uint32_t)bn};
+    uint32_t box[3] = {(uint32_t)BK, 1, (uint32_t)(two ? bn / 2 : bn)};
     int r;
     if ((r = encode_tmap(&a.tmB_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, b_hi, dims, str, box))) return r;
     if ((r = encode_tmap(&a.tmB_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, b_lo, dims, str, box))) return r;
@@ -495,7 +374,13 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   const long long n_tiles = (N + bn - 1) / bn;
   const long long total = m_tiles * n_tiles;
   a.groups = groups;
-  plan->grid = dim3((unsigned)((total < num_sms()) ? total : num_sms()), 1, 1);  // persistent: <= 1 CTA per SM
+  if (two) {
+    const long long pairs = total / 2;
+    const long long clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
+    plan->grid = dim3((unsigned)(2 * clusters), 1, 1);
+  } else {
+    plan->grid = dim3((unsigned)((total < num_sms()) ? total : num_sms()), 1, 1);  // persistent: <= 1 CTA per SM
+  }
   plan->flops = 2.0 * (double)NB * H * W * groups * (double)N * (double)Kc * taps;
   return 0;
 }
@@ -512,8 +397,7 @@ static int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  gemm_bf16x3_kernel<BN><<<plan.grid, kNumThreads, Cfg::SMEM, stream>>>(plan.args);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(gemm_bf16x3_kernel<BN>, plan.grid, dim3(kNumThreads), Cfg::SMEM, stream, plan.args);
   if (e != cudaSuccess) {
     set_error("gemm launch failed: %s", cudaGetErrorString(e));
     return -6;
@@ -522,6 +406,7 @@ static int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  if (plan.two_cta) return gemm2_launch(plan, stream);
   switch (plan.bn) {
     case 64: return launch_bn<64>(plan, stream);
     case 128: return launch_bn<128>(plan, stream);

@@ -58,18 +58,21 @@ struct GemmPlan {
   GemmArgs args;
   dim3 grid;
   int bn;          // 64 / 128 / 256
+  int two_cta;     // 1: 256 x bn tiles on CTA pairs (gemm2.cu)
   double flops;    // algorithmic 2*M*N*K (all groups), for roofline accounting
 };
 
 // Encodes the four tensor maps and picks the tile shape.  Returns 0 or a negative error.
 // lda / ldb: row strides (elements) of A pixels / B rows (0 = dense: Kc resp. taps*Kc);
 // b_group_rows: rows between consecutive groups of B (0 = N).
+// force_bn: 0 = planner's choice; 64/128/256 = 1-CTA kernel with that tile width; 2128/2256 = 2-CTA kernel (256 x 128/256).
 int gemm_plan_init(GemmPlan* plan,
                    const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,   // [G*NB, H, W, Kc]
                    const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,   // [G*N, taps, Kc]
                    int groups, int NB, int H, int W, int Kc, int taps, int N, int force_bn = 0,
                    long long lda = 0, long long ldb = 0, long long b_group_rows = 0);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+int gemm2_launch(const GemmPlan& plan, cudaStream_t stream);   // 2-CTA kernel (gemm2.cu)
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box);

@@ -1,0 +1,330 @@
+// 2-CTA variant of the split-bf16 GEMM engine: a cluster of two CTAs (one TPC) computes a 256 x BN tile
+// with tcgen05.mma.cta_group::2.  Each CTA stages only ITS 128 rows of A and ITS half (BN/2 rows) of B,
+// so the operand bytes every SM pulls through L2 -> SMEM per MMA drop by 1.33x (BN=128) / 1.5x (BN=256)
+// versus the 1-CTA kernel -- and the freed shared memory deepens the TMA ring (4 resp. 3 stages).
+// The GEMM engine is L2->SMEM / latency bound on this path, so that is the lever.
+//
+// Roles per CTA (320 threads): warp 0 TMA producer (both CTAs; completions are counted on the LEADER's
+// full barrier), warp 1 MMA issuer (leader CTA only; commits are multicast to both CTAs' barriers),
+// warps 2..9 epilogue (each CTA drains its own 128 TMEM lanes; two warps per lane quadrant split the columns).
+#include <cstring>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace s3r {
+
+namespace g2 {
+constexpr int BM = 128, BK = 64;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kSmemRing = 192 * 1024;
+}  // namespace g2
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_TILE = g2::BM * g2::BK * 2;      // one plane, this CTA's 128 rows
+  static constexpr int B_TILE = (BN / 2) * g2::BK * 2;    // one plane, this CTA's half of the BN rows
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = g2::kSmemRing / STAGE;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+// ---- cluster / 2-CTA PTX ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// TMA loads whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma2_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive on the same-offset mbarrier of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far -> arrive(1) on the same-offset mbarrier in BOTH CTAs when they retire
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
+    gemm2_bf16x3_kernel(const __grid_constant__ GemmArgs args) {
+  using Cfg = Gemm2Cfg<BN>;
+  using namespace g2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* full_bar = bars;                       // used in the leader only (count 2: both producers)
+  uint64_t* empty_bar = bars + Cfg::STAGES;        // per CTA, multicast commit from the leader
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // per CTA, multicast commit from the leader
+  uint64_t* tmem_empty = tmem_full + 2;            // used in the leader only (count 2 * kEpiWarps)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int n_tiles = (args.N + BN - 1) / BN;
+  const int m_tiles = args.tiles_w * args.tiles_h * args.NB;   // even (host guarantees)
+  const int m_pairs = m_tiles / 2;
+  const int pairs_per_group = n_tiles * m_pairs;
+  const int total_pairs = pairs_per_group * args.groups;
+  const int num_kb = args.taps * args.kpt;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&args.tmA_hi);
+    tma_prefetch_desc(&args.tmA_lo);
+    tma_prefetch_desc(&args.tmB_hi);
+    tma_prefetch_desc(&args.tmB_lo);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        const int g = pt / pairs_per_group;
+        const int rem = pt - g * pairs_per_group;
+        const int mp = rem / n_tiles;
+        const int nt = rem - mp * n_tiles;
+        const int mt = 2 * mp + (int)rank;
+        const int tw = mt % args.tiles_w;
+        const int th = (mt / args.tiles_w) % args.tiles_h;
+        const int nb = mt / (args.tiles_w * args.tiles_h);
+        const int w0 = tw * args.bw, h0 = th * args.bh;
+        const int img = g * args.NB + nb;
+        const int brow = g * args.b_group_rows + nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / args.kpt;
+          const int kc = (kb - tap * args.kpt) * BK;
+          int dx = 0, dy = 0;
+          if (args.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = smem + stage * Cfg::STAGE;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          tma2_load_4d(s, &args.tmA_hi, &full_bar[stage], kc, w0 + dx, h0 + dy, img);
+          tma2_load_4d(s + Cfg::A_TILE, &args.tmA_lo, &full_bar[stage], kc, w0 + dx, h0 + dy, img);
+          tma2_load_3d(s + 2 * Cfg::A_TILE, &args.tmB_hi, &full_bar[stage], kc, tap, brow);
+          tma2_load_3d(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, &full_bar[stage], kc, tap, brow);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(kFmtBF16, 2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+          const uint64_t da_hi = umma_desc_sw128_kmajor(sa);
+          const uint64_t da_lo = umma_desc_sw128_kmajor(sa + Cfg::A_TILE);
+          const uint64_t db_hi = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE);
+          const uint64_t db_lo = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE + Cfg::B_TILE);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ko = (uint64_t)(kk * 32 >> 4);
+            umma2_bf16(tmem_d, da_hi + ko, db_lo + ko, idesc, (kb | kk) != 0);
+            umma2_bf16(tmem_d, da_lo + ko, db_hi + ko, idesc, 1);
+            umma2_bf16(tmem_d, da_hi + ko, db_hi + ko, idesc, 1);
+          }
+          umma2_commit_mc(&empty_bar[stage]);   // frees this smem slot in BOTH CTAs
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_mc(&tmem_full[as]);        // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9), own 128 rows
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;            // column half handled by this warp
+    const int r = quad * 32 + lane;
+    const int dh = r / args.bw, dw = r - dh * args.bw;
+    int it = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int g = pt / pairs_per_group;
+      const int rem = pt - g * pairs_per_group;
+      const int mp = rem / n_tiles;
+      const int nt = rem - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int tw = mt % args.tiles_w;
+      const int th = (mt / args.tiles_w) % args.tiles_h;
+      const int nb = mt / (args.tiles_w * args.tiles_h);
+      const int h = th * args.bh + dh, w = tw * args.bw + dw;
+      const bool valid = (h < args.H) && (w < args.W);
+      const long long pix = ((long long)nb * args.H + h) * args.W + w;
+      const long long grow = (long long)g * args.out_group_rows + pix;
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      float ht_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      constexpr int CH = BN / 64;  // 32-column chunks per warp
+#pragma unroll 1
+      for (int cc = 0; cc < CH; ++cc) {
+        const int c = half * CH + cc;
+        const int col0 = nt * BN + c * 32;
+        if (col0 >= args.N) break;
+        uint32_t raw[32];
+        tmem_ld_32x32(tbase + c * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        epi_chunk(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_remote(&tmem_empty[as], 0);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading our smem through its MMAs / receiving our arrives
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+static int launch2_bn(const GemmPlan& plan, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm2_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return -5;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = plan.grid;
+  cfg.blockDim = dim3(g2::kThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool use_pdl = (getenv("S3R_NO_PDL") == nullptr);
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_kernel<BN>, plan.args);
+  if (e != cudaSuccess) {
+    set_error("gemm2 launch failed: %s", cudaGetErrorString(e));
+    return -6;
+  }
+  return 0;
+}
+
+int gemm2_launch(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.bn) {
+    case 128: return launch2_bn<128>(plan, stream);
+    case 256: return launch2_bn<256>(plan, stream);
+  }
+  set_error("gemm2_launch: bad bn %d", plan.bn);
+  return -1;
+}
+
+}  // namespace s3r

@@ -19,6 +19,8 @@ namespace s3r {
 __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restrict__ S, long long ldS, int M, int Mpad,
                                                           float scale, float thresh, __nv_bfloat16* __restrict__ phi,
                                                           __nv_bfloat16* __restrict__ plo, long long ldP) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float row[];
   __shared__ float red[8];
   const long long r = blockIdx.x;
@@ -90,7 +92,7 @@ int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int
     cudaFuncSetAttribute(mem_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = 200 * 1024;
   }
-  mem_softmax_kernel<<<(unsigned)rows, 256, smem, st>>>(S, ldS, M, Mpad, scale, thresh, phi, plo, ldP);
+  launch_pdl(mem_softmax_kernel, dim3((unsigned)rows), dim3(256), smem, st, S, ldS, M, Mpad, scale, thresh, phi, plo, ldP);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -100,6 +102,8 @@ int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int
 // ------------------------------------------------------------------------------------------------
 __global__ void mem_colsum_kernel(const __nv_bfloat16* __restrict__ phi, const __nv_bfloat16* __restrict__ plo,
                                   long long ldP, int nq, int M, float* __restrict__ mem_attn, long long ld_attn) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (m >= M) return;
@@ -114,7 +118,7 @@ int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long l
                       float* mem_attn, long long ld_attn, cudaStream_t st) {
   if (M == 0) return 0;
   dim3 grid((M + 127) / 128, B);
-  mem_colsum_kernel<<<grid, 128, 0, st>>>(phi, plo, ldP, nq, M, mem_attn, ld_attn);
+  launch_pdl(mem_colsum_kernel, dim3(grid), dim3(128), 0, st, phi, plo, ldP, nq, M, mem_attn, ld_attn);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -125,6 +129,8 @@ int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long l
 __global__ void split_transpose_kernel(const float* __restrict__ x, int T, int C, __nv_bfloat16* __restrict__ ohi,
                                        __nv_bfloat16* __restrict__ olo, long long ldo, long long out_batch_stride,
                                        int col0) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -150,7 +156,7 @@ int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* o
                            long long out_batch_stride, int col0, cudaStream_t st) {
   if (B * T * C == 0) return 0;
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  split_transpose_kernel<<<grid, block, 0, st>>>(x, T, C, ohi, olo, ldo, out_batch_stride, col0);
+  launch_pdl(split_transpose_kernel, dim3(grid), dim3(block), 0, st, x, T, C, ohi, olo, ldo, out_batch_stride, col0);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -161,6 +167,8 @@ int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* o
 // ------------------------------------------------------------------------------------------------
 __global__ void cos_rows_kernel(const float* __restrict__ feat, const float* __restrict__ wm, long long wm_batch_stride,
                                 int B, int T, int P, int C, float* __restrict__ cosv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)B * T * P;
   if (w >= total) return;
@@ -187,6 +195,8 @@ __global__ void cos_rows_kernel(const float* __restrict__ feat, const float* __r
 }
 
 __global__ void mean_rows_kernel(const float* __restrict__ cosv, int P, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[256];
   const float* c = cosv + (long long)blockIdx.x * P;
   float s = 0.f;
@@ -205,8 +215,8 @@ int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stri
   if (B * T * P == 0) return 0;
   if (C % 4) { set_error("check_sim: C %% 4 != 0"); return -1; }
   const long long total = (long long)B * T * P;
-  cos_rows_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(feat, wm, wm_batch_stride, B, T, P, C, scratch);
-  mean_rows_kernel<<<B * T, 256, 0, st>>>(scratch, P, out);
+  launch_pdl(cos_rows_kernel, dim3((unsigned)((total + 7) / 8)), dim3(256), 0, st, feat, wm, wm_batch_stride, B, T, P, C, scratch);
+  launch_pdl(mean_rows_kernel, dim3(B * T), dim3(256), 0, st, scratch, P, out);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

@@ -43,6 +43,9 @@ def test_split_roundtrip(L):
     (300, 96, 1536, 1, 0), (768, 768, 768, 2, 0), (768, 1792, 1792, 2, 0),
     (1000, 512, 512, 1, 64), (1000, 512, 512, 1, 128), (1000, 512, 512, 1, 256), (7680, 1024, 1024, 1, 0),
     (130, 64, 32, 1, 0),
+    # 2-CTA (cta_group::2) kernel, 256 x 128 / 256 x 256 pair tiles
+    (768, 1024, 3072, 1, 2128), (768, 1024, 3072, 1, 2256), (768, 768, 768, 2, 2128), (7680, 1024, 1024, 1, 2256),
+    (1536, 768, 96, 1, 2128), (768, 4096, 1024, 1, 2256),
 ])
 def test_linear_bias_gelu_residual(L, rows, K, N, groups, bn):
     x = _rand(groups * rows, K, seed=2)
