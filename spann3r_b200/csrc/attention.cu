@@ -7,13 +7,9 @@
 // (2-D RoPE), Q pre-scaled by 64^-0.5, V transposed, all rounded to tf32 by the QKV-projection GEMM
 // epilogue (gemm.cu, EPI_QKV), so RoPE never exists as a separate op or tensor.
 //
-// One CTA per (128-query tile, batch*head); 192 threads:
-//   warp 0     TMA: Q tile once, then per 128-key block K (2 boxes) and V^T (4 boxes) into a 2-stage ring
-//   warp 1     MMA issuer: S_j = Q K_j^T  (M128 N128 K64, 8 x tcgen05.mma kind::tf32) into TMEM (double
-//              buffered), then O_j = P_j V_j (M128 N64 K128, 16 MMAs) into a second TMEM region
-//   warps 2-5  softmax, thread = query row: tcgen05.ld S (two passes: max, exp), running max / sum in
-//              registers, P_j written to smem as the tf32 A operand (128B-swizzled by hand), and the
-//              per-block O_j folded into a register accumulator  o = o*alpha + O_j  (no TMEM rescale pass).
+// One CTA per (128-query tile, batch*head), 384 threads: warp 0 TMA (Q once, K / V^T per 128-key block into a
+// 3-stage ring), warp 1 MMA issuer, warpgroups 1 and 2 = two softmax groups that take alternate KV blocks
+// (see the kernel comment).  S, P and O live in TMEM; P is the TMEM A operand of the PV MMA.
 // Output: split-bf16 planes (A operand of the following projection GEMM) and/or fp32.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -29,29 +25,58 @@ constexpr int D = 64;
 constexpr int Q_BYTES = BQ * D * 4;       // 32 KB (2 swizzle atoms of [128 x 32 f32])
 constexpr int K_BYTES = BKV * D * 4;      // 32 KB
 constexpr int V_BYTES = D * BKV * 4;      // 32 KB (4 atoms of [64 x 32 f32])
-constexpr int P_BYTES = BQ * BKV * 4;     // 64 KB (4 atoms of [128 x 32 f32])
-constexpr int KV_STAGES = 2;
-constexpr int SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 128;
-constexpr uint32_t TMEM_COLS = 512;       // S0 [0,128) S1 [128,256) O [256,320)
-constexpr int kThreads = 192;
+constexpr int KV_STAGES = 3;
+constexpr int SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 512;       // group g: S/P at [g*192, +128), O at [g*192+128, +64)
+constexpr int kThreads = 384;             // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1, 2: softmax
 }  // namespace attn
 
+// TMEM <- registers (this warp's 32 lanes x 32 columns)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T, tf32: A = 128 lanes x 8 columns (one fp32 column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
+// One CTA per (128-query tile, batch*head).  The KV blocks alternate between two softmax warpgroups (even blocks ->
+// group 0, odd -> group 1), each with its own S/P and O regions in TMEM and its own running (max, sum, o[64]) state;
+// while one group runs its softmax the tensor core serves the other group's QK^T / PV, and the two partial results
+// are merged once at the end (flash-decoding style).  P never touches shared memory: the softmax threads overwrite
+// their S row in TMEM with tf32 probabilities (tcgen05.st) and the PV MMA takes its A operand from TMEM.
 __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
   using namespace attn;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;                            // stage s: K at s*(K+V), V after K
-  uint8_t* sP = sKV + KV_STAGES * (K_BYTES + V_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KV_STAGES * (K_BYTES + V_BYTES));
   uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // 2
-  uint64_t* kv_empty = bars + 3;      // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* p_full = bars + 7;        // 1 (128 arrivals)
-  uint64_t* o_full = bars + 8;        // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars + 1;       // 3
+  uint64_t* kv_empty = bars + 4;      // 3
+  uint64_t* s_full = bars + 7;        // 2 (per group)
+  uint64_t* p_full = bars + 9;        // 2 (per group, 128 arrivals)
+  uint64_t* o_full = bars + 11;       // 2 (per group)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -67,10 +92,11 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
@@ -81,6 +107,9 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
   pdl_launch_dependents();
   pdl_wait();
 
+  // register re-balancing: the TMA / MMA warpgroup needs few registers, each softmax thread holds a 128-key row
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, Q_BYTES);
@@ -103,154 +132,183 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(kFmtTF32, BQ, BKV);
       constexpr uint32_t idesc_o = umma_idesc(kFmtTF32, BQ, D);
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      const uint32_t tmem_o = tmem_base + 256;
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_s = [&](int j) {   // S_g = Q K_j^T, g = j & 1
+        const int st = j % KV_STAGES;
+        mbar_wait(&kv_full[st], (j / KV_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t aK = smem_u32(sKV + st * (K_BYTES + V_BYTES));
+        const uint32_t tmem_s = tmem_base + (j & 1) * 192;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const uint64_t dq = umma_desc_sw128_kmajor(aQ + a * (Q_BYTES / 2));
+          const uint64_t dk = umma_desc_sw128_kmajor(aK + a * (K_BYTES / 2));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, (a | kk) != 0);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
       mbar_wait(q_full, 0);
-      for (int j = 0; j <= nblk; ++j) {
-        if (j < nblk) {
-          const int st = j % KV_STAGES;
-          mbar_wait(&kv_full[st], (j / KV_STAGES) & 1);
-          tc_fence_after_sync();
-          const uint32_t aK = smem_u32(sKV + st * (K_BYTES + V_BYTES));
-          const uint32_t tmem_s = tmem_base + (j & 1) * BKV;
+      issue_s(0);
+      if (nblk > 1) issue_s(1);
+      for (int j = 0; j < nblk; ++j) {
+        const int g = j & 1;
+        const int st = j % KV_STAGES;
+        mbar_wait(&p_full[g], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t aV = smem_u32(sKV + st * (K_BYTES + V_BYTES) + K_BYTES);
+        const uint32_t tmem_p = tmem_base + g * 192, tmem_o = tmem_p + 128;
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t dq = umma_desc_sw128_kmajor(aQ + a * (Q_BYTES / 2));
-            const uint64_t dk = umma_desc_sw128_kmajor(aK + a * (K_BYTES / 2));
+        for (int a = 0; a < 4; ++a) {
+          const uint64_t dv = umma_desc_sw128_kmajor(aV + a * (V_BYTES / 4));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)  // 8 tf32 = 32 bytes per K step
-              umma_tf32(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, (a | kk) != 0);
-          }
-          umma_commit(&s_full[j & 1]);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32_ts(tmem_o, tmem_p + a * 32 + kk * 8, dv + 2 * kk, idesc_o, (j >= 2) || (a | kk) != 0);
         }
-        if (j >= 1) {
-          const int jj = j - 1;
-          const int st = jj % KV_STAGES;
-          mbar_wait(p_full, jj & 1);
-          tc_fence_after_sync();
-          const uint32_t aV = smem_u32(sKV + st * (K_BYTES + V_BYTES) + K_BYTES);
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const uint64_t dp = umma_desc_sw128_kmajor(aP + a * (P_BYTES / 4));
-            const uint64_t dv = umma_desc_sw128_kmajor(aV + a * (V_BYTES / 4));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_o, dp + 2 * kk, dv + 2 * kk, idesc_o, (a | kk) != 0);
-          }
-          umma_commit(o_full);
-          umma_commit(&kv_empty[st]);
-        }
+        umma_commit(&o_full[g]);
+        umma_commit(&kv_empty[st]);
+        if (j + 2 < nblk) issue_s(j + 2);   // same group's next block: its S/P columns are free once PV_j retires
       }
     }
+  }
   } else {
-    // ------------------------------------------------------------------ softmax warps, thread = query row
+    // ------------------------------------------------------------------ softmax groups, thread = query row
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    uint8_t* prow = sP + r * 128;
-    const int sw = r & 7;
-
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+    const uint32_t ts = tmem_base + lane_sel + g * 192;     // S / P
+    const uint32_t to = ts + 128;                           // O
+    // Exact online softmax with a lazily updated reference (FA4-style): p = exp(s - ref), where ref only moves when
+    // a block's row max exceeds it by more than 8 (p <= e^8 stays far from overflow); l and the TMEM-resident O
+    // accumulator are rescaled in the same step, so the result is exact regardless of the threshold.
+    constexpr float kLog2e = 1.4426950408889634f;
+    float ref = -INFINITY, l = 0.f;
+    int it = 0;
+    for (int j = g; j < nblk; j += 2, ++it) {
+      mbar_wait(&s_full[g], it & 1);
       tc_fence_after_sync();
-      const uint32_t ts = tmem_base + lane_sel + (j & 1) * BKV;
       const int kbase = j * BKV;
-      // pass 1: block max
-      float bmax = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(ts + c * 32, raw);
-        tmem_ld_wait();
+      uint32_t s0[32], s1[32], s2[32], s3[32];   // the whole 128-key row of S: read from TMEM exactly once
+      tmem_ld_32x32(ts, s0);
+      tmem_ld_32x32(ts + 32, s1);
+      tmem_ld_32x32(ts + 64, s2);
+      tmem_ld_32x32(ts + 96, s3);
+      tmem_ld_wait();
+      if (kbase + BKV > args.nk) {   // ragged last block: keys beyond nk do not exist
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float s = (kbase + c * 32 + i < args.nk) ? __uint_as_float(raw[i]) : -INFINITY;
-          bmax = fmaxf(bmax, s);
+          if (kbase + i >= args.nk) s0[i] = 0xff800000u;
+          if (kbase + 32 + i >= args.nk) s1[i] = 0xff800000u;
+          if (kbase + 64 + i >= args.nk) s2[i] = 0xff800000u;
+          if (kbase + 96 + i >= args.nk) s3[i] = 0xff800000u;
         }
       }
-      const float m_new = fmaxf(m, bmax);
-      const float alpha = __expf(m - m_new);  // first block: exp(-inf) = 0
-      // retire the previous block's P.V into the register accumulator (also proves sP is free again)
-      if (j >= 1) {
-        mbar_wait(o_full, (j - 1) & 1);
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        bmax = fmaxf(bmax, fmaxf(fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])),
+                                 fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i]))));
+      }
+      if (it == 0) {
+        ref = bmax;
+      } else if (__any_sync(0xffffffffu, bmax > ref + 8.0f)) {   // rare: move the reference, rescale l and O
+        const float new_ref = (bmax > ref + 8.0f) ? bmax : ref;
+        const float alpha = exp2f((ref - new_ref) * kLog2e);
+        mbar_wait(&o_full[g], (it - 1) & 1);   // this group's previous P.V has retired
         tc_fence_after_sync();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + lane_sel + 256 + c * 32, raw);
+          tmem_ld_32x32(to + c * 32, raw);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+          tmem_st_32x32(to + c * 32, raw);
         }
+        l *= alpha;
+        ref = new_ref;
       }
-      // pass 2: p = exp(s - m_new), row sum, P tile (tf32) into swizzled smem
+      const float nref2 = -ref * kLog2e;
       float psum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      auto expo = [&](uint32_t (&x)[32]) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(fmaf(__uint_as_float(x[i]), kLog2e, nref2));   // exp(s - ref); exp(-inf) = 0
+          const uint32_t rb = (__float_as_uint(e) + 0x1000u) & 0xffffe000u;     // round to tf32 (the MMA truncates)
+          psum += __uint_as_float(rb);
+          x[i] = rb;
+        }
+      };
+      expo(s0); tmem_st_32x32(ts, s0);          // P overwrites S in place
+      expo(s1); tmem_st_32x32(ts + 32, s1);
+      expo(s2); tmem_st_32x32(ts + 64, s2);
+      expo(s3); tmem_st_32x32(ts + 96, s3);
+      tmem_st_wait();
+      l += psum;
+      tc_fence_before_sync();
+      mbar_arrive(&p_full[g]);
+    }
+    float m = ref;
+    float o[D];
+    if (it >= 1) {
+      mbar_wait(&o_full[g], (it - 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        tmem_ld_32x32(ts + c * 32, raw);
+        tmem_ld_32x32(to + c * 32, raw);
         tmem_ld_wait();
-        float p[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(raw[i]);
-          float e = (kbase + c * 32 + i < args.nk) ? __expf(s - m_new) : 0.f;
-          e = to_tf32(e);
-          psum += e;
-          p[i] = e;
-        }
-        uint8_t* pa = prow + c * (P_BYTES / 4);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(pa + ((q ^ sw) << 4)) = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
       }
-      l = l * alpha + psum;
-      m = m_new;
-      alpha_prev = alpha;
-      tc_fence_before_sync();   // our tcgen05.ld of S_j are done before the MMA warp may overwrite the buffer
-      fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(p_full);
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) o[i] = 0.f;
     }
-    // last block
-    mbar_wait(o_full, (nblk - 1) & 1);
-    tc_fence_after_sync();
+    // ---- merge the two groups' partial results through shared memory (the KV ring is drained by now) ----
+    float* mg = reinterpret_cast<float*>(sKV);        // [66][128]: o[0..63], m, l  (column = query row)
+    named_bar_sync(1, 256);   // both groups have seen their last o_full: every MMA that reads the KV ring has retired
+    if (g == 1) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + lane_sel + 256 + c * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(raw[i]));
+      for (int i = 0; i < D; ++i) mg[i * 128 + r] = o[i];
+      mg[64 * 128 + r] = m;
+      mg[65 * 128 + r] = l;
     }
-    const int q = q0 + r;
-    if (q < args.nq) {
-      const float inv = 1.0f / l;
-      const int b = bh / args.heads, h = bh - b * args.heads;
-      const long long off = ((long long)b * args.nq + q) * args.ldo + h * D;
-      if (args.o_f32) {
+    named_bar_sync(1, 256);
+    if (g == 0) {
+      const float m1 = mg[64 * 128 + r], l1 = mg[65 * 128 + r];
+      const float mm = fmaxf(m, m1);
+      const float w0 = __expf(m - mm), w1 = (l1 > 0.f) ? __expf(m1 - mm) : 0.f;
+      const float inv = 1.0f / (l * w0 + l1 * w1);
 #pragma unroll
-        for (int i = 0; i < D; i += 4)
-          st_f4(args.o_f32 + off + i, o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
-      }
-      if (args.o_hi) {
-        uint32_t ph[32], pl[32];
+      for (int i = 0; i < D; ++i) o[i] = (o[i] * w0 + mg[i * 128 + r] * w1) * inv;
+      const int q = q0 + r;
+      if (q < args.nq) {
+        const int b = bh / args.heads, h = bh - b * args.heads;
+        const long long off = ((long long)b * args.nq + q) * args.ldo + h * D;
+        if (args.o_f32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          __nv_bfloat16 ah, al, bh2, bl;
-          split_bf16(o[2 * i] * inv, ah, al);
-          split_bf16(o[2 * i + 1] * inv, bh2, bl);
-          ph[i] = pack_bf16(ah, bh2);
-          pl[i] = pack_bf16(al, bl);
+          for (int i = 0; i < D; i += 4) st_f4(args.o_f32 + off + i, o[i], o[i + 1], o[i + 2], o[i + 3]);
         }
-        uint4* hp = reinterpret_cast<uint4*>(args.o_hi + off);
-        uint4* lp = reinterpret_cast<uint4*>(args.o_lo + off);
+        if (args.o_hi) {
+          uint32_t ph[32], pl[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          hp[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-          lp[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+          for (int i = 0; i < 32; ++i) {
+            __nv_bfloat16 ah, al, bh2, bl;
+            split_bf16(o[2 * i], ah, al);
+            split_bf16(o[2 * i + 1], bh2, bl);
+            ph[i] = pack_bf16(ah, bh2);
+            pl[i] = pack_bf16(al, bl);
+          }
+          uint4* hp = reinterpret_cast<uint4*>(args.o_hi + off);
+          uint4* lp = reinterpret_cast<uint4*>(args.o_lo + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            hp[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+            lp[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+          }
         }
       }
     }
