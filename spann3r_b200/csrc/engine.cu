@@ -7,6 +7,7 @@
 #include "../../include/spann3r_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <utility>
@@ -56,7 +57,20 @@ struct PlanCache {
   size_t gc = 0, ac = 0;
   bool building = true;
   void begin() { gc = ac = 0; }
-  void end() { building = false; }
+  void end() {
+    if (building) {
+      // chain: every GEMM prefetches the weight planes of the next GEMM of the stage into L2 (<= 32 MB each)
+      static const bool on = (getenv("S3R_PREFETCH") != nullptr);   // measured: no gain on B200 (-1%), off by default
+      for (size_t i = 0; on && i + 1 < gemms.size(); ++i) {
+        const GemmPlan& nx = gemms[i + 1];
+        if (nx.b_bytes == 0 || nx.b_bytes > (32ull << 20)) continue;
+        gemms[i].args.pf_base0 = (const unsigned char*)nx.b_hi;
+        gemms[i].args.pf_base1 = (const unsigned char*)nx.b_lo;
+        gemms[i].args.pf_bytes = nx.b_bytes;
+      }
+    }
+    building = false;
+  }
 };
 
 }  // namespace

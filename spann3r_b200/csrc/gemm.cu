@@ -167,6 +167,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    if (args.pf_bytes) {   // pull the next GEMM's weights into L2 while this kernel's main loop runs
+      const unsigned long long lines = args.pf_bytes >> 7;
+      for (unsigned long long ln = (unsigned long long)blockIdx.x * 128 + (threadIdx.x - 64); ln < lines;
+           ln += (unsigned long long)gridDim.x * 128) {
+        prefetch_l2(args.pf_base0 + (ln << 7));
+        prefetch_l2(args.pf_base1 + (ln << 7));
+      }
+    }
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
     const int dh = r / args.bw, dw = r - dh * args.bw;
@@ -382,6 +390,8 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
     plan->grid = dim3((unsigned)((total < num_sms()) ? total : num_sms()), 1, 1);  // persistent: <= 1 CTA per SM
   }
   plan->flops = 2.0 * (double)NB * H * W * groups * (double)N * (double)Kc * taps;
+  plan->b_hi = b_hi; plan->b_lo = b_lo;
+  plan->b_bytes = (unsigned long long)(b_group_rows * (groups - 1) + N) * (unsigned long long)ldb * 2ull;
   return 0;
 }
 

@@ -125,3 +125,30 @@ def test_batched_sequences_match_single(models):
         for k in pa[i]:
             assert rel_l2(pboth[i][k][0:1].cpu(), pa[i][k].cpu()) < 1e-5, (i, k)
             assert rel_l2(pboth[i][k][1:2].cpu(), pb[i][k].cpu()) < 1e-5, (i, k)
+
+
+def test_long_sequence_with_prune_vs_oracle(models):
+    """30 frames at 224x224 (196 tokens/frame): the bank passes long_mem_size=4000 and is pruned (top-k by attention
+    weight, spann3r/model.py:185-210).  Compared with the oracle run on the same GPU in strict fp32; the top-k
+    membership near the cut can legitimately flip on 1e-5-level differences, so the bar is
+    the north-star 1e-3 on the median frame and 5e-3 on the worst."""
+    from oracle import spann3r_oracle as orc
+    from spann3r_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = models[True]
+    sd = {k: v.cuda() for k, v in get_state_dict(True).items()}
+    frames = synth.make_frames(30, 224, 224)
+    preds, _, mem = m(frames, return_memory=True)
+    ref, _, omem = orc.forward(sd, [{"img": f["img"].cuda()} for f in frames], return_memory=True)
+    torch.cuda.synchronize()
+    assert mem.bank.len == omem.mem_k.shape[1] and mem.wm == omem.wm and mem.lm == omem.lm
+    assert mem.bank.len < 30 * 196          # a prune happened
+    errs = []
+    for p, r in zip(preds, ref):
+        k = "pts3d" if "pts3d" in r else "pts3d_in_other_view"
+        errs.append(rel_l2(p[k].cpu(), r[k].cpu()))
+    errs_sorted = sorted(errs)
+    print("per-frame rel-L2:", ["%.1e" % e for e in errs])
+    assert errs_sorted[len(errs) // 2] < 1e-3, errs
+    assert errs_sorted[-1] < 5e-3, errs
