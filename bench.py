@@ -89,6 +89,12 @@ def run_reference(args):
     from oracle import spann3r_oracle as orc
     from spann3r_b200 import synth
     nf = 3
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm is entitled to every host core
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), avail // 2 if avail >= 4 else avail))
     sd = synth.make_state_dict(sharpen=True)
     frames = synth.make_frames(nf, HEIGHT, WIDTH)
     cores = torch.get_num_threads()
@@ -119,6 +125,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--batch", type=int, default=1,
+                    help="sequences advanced in lockstep per GPU (BASELINE config[2] runs 8 per GPU); the headline is 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -140,8 +148,10 @@ def main():
     model = model.to(dev).eval()
 
     # per-rank independent sequences (seeds differ per rank and per step)
+    BATCH = max(1, args.batch)
+
     def host_frames(step):
-        fr = synth.make_frames(F_, HEIGHT, WIDTH, seed0=1 + 1000 * rank + 100 * step)
+        fr = synth.make_frames(F_, HEIGHT, WIDTH, batch=BATCH, seed0=1 + 1000 * rank + 100 * step)
         return [{"img": f["img"].pin_memory()} for f in fr]
 
     n_distinct = 2
@@ -166,7 +176,7 @@ def main():
     # ---- warm-up (also builds every tensor map / plan) ----
     for i in range(W_):
         model(resident[i % n_distinct])
-    eng = model._engine_for(1, HEIGHT, WIDTH, n_frames=F_)
+    eng = model._engine_for(BATCH, HEIGHT, WIDTH, n_frames=F_)
     torch.cuda.synchronize(dev)
 
     # ---- timed: inputs resident in HBM ----
@@ -185,7 +195,7 @@ def main():
     launches = eng.take_launches()
     flops_issued = eng.take_flops()
     clocks = sampler.stop() if rank == 0 else None
-    value = world * F_ * K / (ms / 1e3)
+    value = world * BATCH * F_ * K / (ms / 1e3)
 
     # ---- timed: end to end through the public API, pinned host inputs -> device, predictions -> pinned host ----
     def e2e_step(seq_host):
@@ -208,9 +218,9 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    h2d = F_ * 3 * HEIGHT * WIDTH * 4
+    h2d = BATCH * F_ * 3 * HEIGHT * WIDTH * 4
     d2h = sum(o.numel() * 4 for o in outs)
-    e2e = world * F_ * K / (ms_e2e / 1e3)
+    e2e = world * BATCH * F_ * K / (ms_e2e / 1e3)
 
     # ---- roofline leg: per-launch CUDA-event timing of the tensor-core kernels (separate, untimed pass) ----
     eng.profile(True)
@@ -236,7 +246,7 @@ def main():
         "gemm_flops_per_launch": prof["gemm_flops"] / max(prof["gemm_launches"], 1),
         "attention_ms_per_seq": prof["attn_ms"], "attention_tflops": (prof["attn_flops"] / (prof["attn_ms"] * 1e-3) / 1e12
                                                                        if prof["attn_ms"] > 0 else 0.0),
-        "whole_path_frac": (FLOP_PER_SEQ * F_ / FRAMES * K * world / (ms / 1e3)) / 1e12 / pk["bf16_sustained"] / world,
+        "whole_path_frac": (FLOP_PER_SEQ * BATCH * F_ / FRAMES * K * world / (ms / 1e3)) / 1e12 / pk["bf16_sustained"] / world,
     }
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) ----
@@ -256,7 +266,7 @@ def main():
             "metric": "frames/sec (512x384, 10-frame seq) enc->mem-attn->dec->DPT", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; tf32 attention)", "data": "synthetic",
-            "config": {"workload": f"{F_}-frame {WIDTH}x{HEIGHT} sequence per step, batch 1 per GPU, ViT-L enc / ViT-B dec + DPT, "
+            "config": {"workload": f"{F_}-frame {WIDTH}x{HEIGHT} sequence per step, batch {BATCH} per GPU, ViT-L enc / ViT-B dec + DPT, "
                                    "random-init sharpened checkpoint (SURVEY.md §8d config 2)",
                        "parallelism": f"{world} independent replicas (one sequence stream per GPU, no collective)",
                        "l2": "per-step working set (2.6 GB packed weights + activations) >> 126 MB L2; inputs alternate between "
