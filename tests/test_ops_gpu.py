@@ -46,6 +46,8 @@ def test_split_roundtrip(L):
     # 2-CTA (cta_group::2) kernel, 256 x 128 / 256 x 256 pair tiles
     (768, 1024, 3072, 1, 2128), (768, 1024, 3072, 1, 2256), (768, 768, 768, 2, 2128), (7680, 1024, 1024, 1, 2256),
     (1536, 768, 96, 1, 2128), (768, 4096, 1024, 1, 2256),
+    # K-heavy shapes with few tiles (value-encoder fc2, decoder fc2, tiny-M long-K)
+    (768, 4096, 1024, 1, 0), (768, 3072, 768, 2, 0), (256, 6912, 768, 2, 0), (196, 1024, 1024, 1, 0),
 ])
 def test_linear_bias_gelu_residual(L, rows, K, N, groups, bn):
     x = _rand(groups * rows, K, seed=2)
@@ -65,7 +67,7 @@ def test_linear_bias_gelu_residual(L, rows, K, N, groups, bn):
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,groups", [
     (1, 12, 16, 256, 256, 2), (1, 24, 32, 96, 256, 1), (2, 7, 7, 256, 256, 1), (1, 96, 128, 256, 128, 2),
-    (1, 14, 14, 384, 256, 1), (1, 48, 64, 192, 256, 1),
+    (1, 14, 14, 384, 256, 1), (1, 48, 64, 192, 256, 1), (1, 12, 16, 768, 256, 2),
 ])
 def test_conv3x3(L, NB, H, W, Cin, Cout, groups):
     x = _rand(groups * NB, Cin, H, W, seed=6)
