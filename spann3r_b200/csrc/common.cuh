@@ -48,7 +48,9 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float gelu_erf(float x) {
+// not inlined on purpose: the unrolled epilogues call it 32x per chunk and erff is ~100 instructions; keeping the GEMM
+// kernels small (instruction cache) matters more than the call overhead in the epilogue warps
+static __device__ __noinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 

@@ -46,7 +46,7 @@ struct GemmCfg {
 };
 
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -210,14 +210,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-        epi_chunk(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+        epi_chunk<EPI>(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
       }
       // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
 
-      if (args.epi == EPI_HEADTAIL && valid) {
+      if (EPI == EPI_HEADTAIL && valid) {
         const float* b4 = args.ht_b + g * 4;
         const float x = ht_acc[0] + b4[0], y = ht_acc[1] + b4[1], z = ht_acc[2] + b4[2], cf = ht_acc[3] + b4[3];
         const float d = sqrtf(x * x + y * y + z * z);
@@ -395,19 +395,20 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   return 0;
 }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
       return -5;
     }
     attr_set = true;
   }
-  cudaError_t e = launch_pdl(gemm_bf16x3_kernel<BN>, plan.grid, dim3(kNumThreads), Cfg::SMEM, stream, plan.args);
+  cudaError_t e = launch_pdl(gemm_bf16x3_kernel<BN, EPI>, plan.grid, dim3(kNumThreads), Cfg::SMEM, stream, plan.args);
   if (e != cudaSuccess) {
     set_error("gemm launch failed: %s", cudaGetErrorString(e));
     return -6;
@@ -415,12 +416,24 @@ static int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
   return 0;
 }
 
+template <int BN>
+static int launch_epi(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.args.epi) {
+    case EPI_PLAIN: return launch_bn<BN, EPI_PLAIN>(plan, stream);
+    case EPI_PIXSHUF: return launch_bn<BN, EPI_PIXSHUF>(plan, stream);
+    case EPI_QKV: return launch_bn<BN, EPI_QKV>(plan, stream);
+    case EPI_HEADTAIL: return launch_bn<BN, EPI_HEADTAIL>(plan, stream);
+  }
+  set_error("gemm_launch: bad epilogue mode %d", plan.args.epi);
+  return -1;
+}
+
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.two_cta) return gemm2_launch(plan, stream);
   switch (plan.bn) {
-    case 64: return launch_bn<64>(plan, stream);
-    case 128: return launch_bn<128>(plan, stream);
-    case 256: return launch_bn<256>(plan, stream);
+    case 64: return launch_epi<64>(plan, stream);
+    case 128: return launch_epi<128>(plan, stream);
+    case 256: return launch_epi<256>(plan, stream);
   }
   set_error("gemm_launch: bad bn %d", plan.bn);
   return -1;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
       : "memory");
 }
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
     gemm2_bf16x3_kernel(const __grid_constant__ GemmArgs args) {
   using Cfg = Gemm2Cfg<BN>;
@@ -269,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epi_chunk(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+        epi_chunk<EPI>(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -290,13 +290,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int EPI>
 static int launch2_bn(const GemmPlan& plan, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(gemm2_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaFuncSetAttribute(gemm2_bf16x3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM, cudaGetErrorString(e));
       return -5;
@@ -318,7 +318,7 @@ static int launch2_bn(const GemmPlan& plan, cudaStream_t stream) {
   static const bool use_pdl = (getenv("S3R_NO_PDL") == nullptr);
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_kernel<BN>, plan.args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_kernel<BN, EPI>, plan.args);
   if (e != cudaSuccess) {
     set_error("gemm2 launch failed: %s", cudaGetErrorString(e));
     return -6;
@@ -326,10 +326,21 @@ static int launch2_bn(const GemmPlan& plan, cudaStream_t stream) {
   return 0;
 }
 
+template <int BN>
+static int launch2_epi(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.args.epi) {
+    case EPI_PLAIN: return launch2_bn<BN, EPI_PLAIN>(plan, stream);
+    case EPI_PIXSHUF: return launch2_bn<BN, EPI_PIXSHUF>(plan, stream);
+    case EPI_QKV: return launch2_bn<BN, EPI_QKV>(plan, stream);
+  }
+  set_error("gemm2_launch: epilogue mode %d is not available on the 2-CTA kernel", plan.args.epi);
+  return -1;
+}
+
 int gemm2_launch(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.bn) {
-    case 128: return launch2_bn<128>(plan, stream);
-    case 256: return launch2_bn<256>(plan, stream);
+    case 128: return launch2_epi<128>(plan, stream);
+    case 256: return launch2_epi<256>(plan, stream);
   }
   set_error("gemm2_launch: bad bn %d", plan.bn);
   return -1;

@@ -14,12 +14,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // v: 32 accumulator values (columns col0 .. col0+31 of group g); (nb, h, w): the row's pixel; pix: row index inside the
 // group; grow: global output row for EPI_PLAIN; ht_acc: running 1x1-conv dot products of EPI_HEADTAIL.
+template <int EPI>
 __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], int g, int nb, int h, int w, bool valid,
                                           long long pix, long long grow, int col0, float (&ht_acc)[4]) {
   // bias
   if (args.bias != nullptr) {
-    const int bcol = (args.epi == EPI_PIXSHUF) ? (col0 % args.ps_cout) : col0;
-    const int bstride = (args.epi == EPI_PIXSHUF) ? args.ps_cout : args.N;
+    const int bcol = (EPI == EPI_PIXSHUF) ? (col0 % args.ps_cout) : col0;
+    const int bstride = (EPI == EPI_PIXSHUF) ? args.ps_cout : args.N;
     const float4* bp = reinterpret_cast<const float4*>(args.bias + (long long)g * bstride + bcol);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -35,10 +36,10 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
     for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], args.act);
   }
 
-  if (args.epi == EPI_PLAIN || args.epi == EPI_PIXSHUF) {
+  if constexpr (EPI == EPI_PLAIN || EPI == EPI_PIXSHUF) {
     long long orow = grow;
     int ocol = col0;
-    if (args.epi == EPI_PIXSHUF) {
+    if constexpr (EPI == EPI_PIXSHUF) {
       const int ij = col0 / args.ps_cout;
       ocol = col0 - ij * args.ps_cout;
       const int s = args.ps_s;
@@ -99,7 +100,7 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
         }
       }
     }
-  } else if (args.epi == EPI_QKV) {
+  } else if constexpr (EPI == EPI_QKV) {
     // croco/models/blocks.py:97-104 (self) / :154-160 (cross) + RoPE2D (pos_embed.py:112-159,
     // curope/kernels.cu:18-81): head dim 64 = [y half | x half], each half = 16 (u, v) pairs
     // (j, j+16) rotated by pos * 100^(-j/16).
