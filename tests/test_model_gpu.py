@@ -158,3 +158,30 @@ def test_long_sequence_with_prune_vs_oracle(models):
     print("per-frame rel-L2:", ["%.1e" % e for e in errs])
     assert errs_sorted[len(errs) // 2] < 1e-3, errs
     assert errs_sorted[-1] < 5e-3, errs
+
+
+def test_dust3r_pairwise_forward_and_stage_api(models):
+    """`model.dust3r(view1, view2)` (dust3r/model.py:213-225, used by dust3r.inference.inference) and the
+    `_encode_image` / `_decoder` stage methods return the reference's structures and values."""
+    from oracle import spann3r_oracle as orc
+    from spann3r_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = models[False]
+    sd = {k: v.cuda() for k, v in get_state_dict(False).items()}
+    fr = synth.make_frames(2, 224, 224)
+    res1, res2 = m.dust3r({"img": fr[0]["img"]}, {"img": fr[1]["img"]})
+    assert set(res1) == {"pts3d", "conf"} and set(res2) == {"pts3d_in_other_view", "conf"}
+    img = torch.cat([f["img"] for f in fr]).cuda()
+    feats, pos = orc.encode_image(sd, img)
+    d1, d2 = orc.decoder(sd, feats[:1], pos[:1], feats[1:], pos[1:])
+    r1 = orc.dpt_head(sd, "dust3r.downstream_head1", d1, 224, 224)
+    r2 = orc.dpt_head(sd, "dust3r.downstream_head2", d2, 224, 224)
+    assert rel_l2(res1["pts3d"].cpu(), r1["pts3d"].cpu()) < 1e-3 and rel_l2(res1["conf"].cpu(), r1["conf"].cpu()) < 1e-3
+    assert rel_l2(res2["pts3d_in_other_view"].cpu(), r2["pts3d"].cpu()) < 1e-3
+    x, p, _ = m.dust3r._encode_image(img)
+    assert x.shape == (2, 196, 1024) and p.shape == (2, 196, 2) and p.dtype == torch.int64
+    assert torch.equal(p.cpu(), pos.cpu())
+    dec1, dec2 = m.dust3r._decoder(x[:1].contiguous(), p[:1], x[1:].contiguous(), p[1:])
+    assert len(dec1) == len(dec2) == 13 and dec1[0].shape[-1] == 1024 and dec1[-1].shape == (1, 196, 768)
+    assert rel_l2(dec1[-1].cpu(), d1[-1].cpu()) < 1e-3 and rel_l2(dec2[6].cpu(), d2[6].cpu()) < 1e-3
