@@ -168,13 +168,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(ms):
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+    from spann3r_b200 import shard
+
+    def max_over_ranks(ms):   # spann3r_b200/shard.py (covered by the world_size-2 gloo test)
+        return shard.max_over_ranks(ms, device=dev)
 
     # ---- warm-up (also builds every tensor map / plan) ----
     for i in range(W_):
