@@ -109,6 +109,10 @@ int s3r_gemm_tile_n(const s3r_gemm_desc* d);
 int s3r_attention(const float* q, const float* k, const float* vt, int bh, int heads, int nq, int nk, int nk_pad,
                   void* o_hi, void* o_lo, float* o_f32, int64_t ldo, void* stream);
 
+/* Offline-mode view score: out[0] = mean((conf-1)/conf) over n values (spann3r/model.py:346-352, 372-381);
+ * scratch256 = 256 floats of device scratch.  Deterministic. */
+int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, void* stream);
+
 /* ---- model level: the per-frame forward path -------------------------------------------------
  * Packed weights.  The host (spann3r_b200/weights.py) converts the reference state dict ONCE into
  * split-bf16 planes laid out [groups*N, taps*Kc] (K contiguous) plus fp32 biases / LayerNorm params,

@@ -350,3 +350,87 @@ def forward(sd, frames, return_memory=False, trace=None, **mem_kw):
     if return_memory:
         return preds, preds_all, sp_mem
     return preds, preds_all
+
+
+# ------------------------------------------------------------------------------------------------
+# offline mode: pairwise DUSt3R forward + best-view-first reconstruction
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def dust3r_forward(sd, view1, view2):
+    """AsymmetricCroCo3DStereo.forward, dust3r/model.py:213-225 (the symmetrized-batch shortcut of :156-184 only
+    skips redundant encoder work; the result per pair is the same)."""
+    img1, img2 = view1["img"], view2["img"]
+    B, _, H, W = img1.shape
+    feats, pos = encode_image(sd, torch.cat((img1, img2), dim=0))
+    dec1, dec2 = decoder(sd, feats[:B], pos[:B], feats[B:], pos[B:])
+    res1 = dpt_head(sd, "dust3r.downstream_head1", dec1, H, W)
+    res2 = dpt_head(sd, "dust3r.downstream_head2", dec2, H, W)
+    res2["pts3d_in_other_view"] = res2.pop("pts3d")
+    return res1, res2
+
+
+def conf_score(conf):
+    """mean of (conf-1)/conf, spann3r/model.py:346-352, 372-381."""
+    return ((conf - 1) / conf).mean()
+
+
+def find_initial_pair(graph, n_frames):
+    """spann3r/model.py:333-357."""
+    view1, view2, pred1, pred2 = graph["view1"], graph["view2"], graph["pred1"], graph["pred2"]
+    conf_matrix = torch.zeros(n_frames, n_frames)
+    for i in range(len(view1["idx"])):
+        conf_matrix[view1["idx"][i], view2["idx"][i]] = conf_score(pred1["conf"][i]) + conf_score(pred2["conf"][i])
+    flat = int(conf_matrix.argmax())
+    return flat // n_frames, flat % n_frames
+
+
+@torch.no_grad()
+def offline_reconstruction(sd, frames, graph, **mem_kw):
+    """Spann3R.offline_reconstruction, spann3r/model.py:394-471 (+ find_next_best_view :359-392), eval mode."""
+    n_frames = len(frames)
+    idx_todo = list(range(n_frames))
+    H, W = frames[0]["img"].shape[-2:]
+    sp_mem = SpatialMemory(sd, **mem_kw)
+    p0, p1 = find_initial_pair(graph, n_frames)
+    idx_used = [p0, p1]
+    idx_todo.remove(p0)
+    idx_todo.remove(p1)
+    out, pos = encode_image(sd, torch.cat((frames[p0]["img"], frames[p1]["img"]), dim=0))
+    feat1, feat2 = out.chunk(2, dim=0)
+    pos1, pos2 = pos.chunk(2, dim=0)
+    dec1, dec2 = decoder(sd, feat1, pos1, feat2, pos2)
+    res1 = dpt_head(sd, "dust3r.downstream_head1", dec1, H, W)
+    res2 = dpt_head(sd, "dust3r.downstream_head2", dec2, H, W)
+    feat_k2, preds, preds_all = None, None, []
+    while True:
+        if feat_k2 is not None:
+            feat1, pos1 = feat2, pos2
+            feat_fuse = sp_mem.memory_read(feat_k2, res=True)
+            best_conf, best = 0.0, None
+            for i in idx_todo:   # find_next_best_view
+                f2, ps2 = encode_image(sd, frames[i]["img"])
+                d1, d2 = decoder(sd, feat_fuse, pos1, f2, ps2)
+                r1 = dpt_head(sd, "dust3r.downstream_head1", d1, H, W)
+                r2 = dpt_head(sd, "dust3r.downstream_head2", d2, H, W)
+                total = conf_score(r1["conf"]) + conf_score(r2["conf"])
+                if total > best_conf:
+                    best_conf, best = total, (i, d1, d2, r1, r2, f2, ps2)
+            id_n, dec1, dec2, res1, res2, feat2, pos2 = best
+            idx_todo.remove(id_n)
+            idx_used.append(id_n)
+        feat_k1 = key_head(sd, 1, feat1, dec1[-1])
+        feat_k2 = key_head(sd, 2, feat2, dec2[-1])
+        cur_v = encode_cur_value(sd, res1["pts3d"])
+        sp_mem.add_mem_check(feat_k1, cur_v + feat_k1)
+        res2["pts3d_in_other_view"] = res2.pop("pts3d")
+        if preds is None:
+            preds = [res1]
+            preds_all = [(res1, res2)]
+        else:
+            res1["pts3d_in_other_view"] = res1.pop("pts3d")
+            preds.append(res1)
+            preds_all.append((res1, res2))
+        if len(idx_todo) == 0:
+            break
+    preds.append(res2)
+    return preds, preds_all, idx_used

@@ -50,6 +50,7 @@ _PROTOS = {
     "s3r_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "s3r_gemm_tile_n": (_i, [C.POINTER(GemmDesc)]),
     "s3r_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
+    "s3r_conf_score": (_i, [_vp, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -170,3 +171,12 @@ def linear(x_planes, w_planes, bias=None, act=ACT_NONE, res=None, want_f32=True,
         d.out_hi, d.out_lo, d.ldp = oh.data_ptr(), ol.data_ptr(), N
     gemm(d)
     return out, oh, ol
+
+
+def conf_score(conf: torch.Tensor) -> torch.Tensor:
+    """mean((conf-1)/conf) over all elements, as a 1-element device tensor."""
+    assert conf.is_cuda and conf.dtype == torch.float32 and conf.is_contiguous()
+    scratch = torch.empty(256, dtype=torch.float32, device=conf.device)
+    out = torch.empty(1, dtype=torch.float32, device=conf.device)
+    check(lib().s3r_conf_score(ptr(conf), conf.numel(), ptr(scratch), ptr(out), stream_ptr()), "s3r_conf_score")
+    return out

@@ -115,6 +115,10 @@ int s3r_gemm_tile_n(const s3r_gemm_desc* d) {
   return plan.bn;
 }
 
+int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, void* stream) {
+  return launch_conf_score(conf, n, scratch256, out, S(stream));
+}
+
 int s3r_attention(const float* q, const float* k, const float* vt, int bh, int heads, int nq, int nk, int nk_pad,
                   void* o_hi, void* o_lo, float* o_f32, int64_t ldo, void* stream) {
   return launch_attention(q, k, vt, bh, heads, nq, nk, nk_pad, B(o_hi), B(o_lo), o_f32, ldo, S(stream));

@@ -53,6 +53,8 @@ int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* o
 int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stride, int B, int T, int P, int C,
                      float* scratch, float* out, cudaStream_t st);
 
+int launch_conf_score(const float* conf, long long n, float* scratch256, float* out, cudaStream_t st);
+
 // fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output
 int launch_attention(const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk, int nk_pad,
                      __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo, cudaStream_t st);

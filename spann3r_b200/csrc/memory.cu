@@ -230,4 +230,45 @@ int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stri
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Confidence score of the offline mode (spann3r/model.py:346-352, 372-381): mean over all pixels of
+// (conf - 1) / conf.  Two fixed-shape passes (256 partial sums, then one block): deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conf_partial_kernel(const float* __restrict__ conf, long long n, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[256];
+  float s = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const float c = conf[i];
+    s += (c - 1.0f) / c;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) conf_final_kernel(const float* __restrict__ part, int nparts, long long n, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[256];
+  red[threadIdx.x] = threadIdx.x < nparts ? part[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0] / (float)n;
+}
+
+int launch_conf_score(const float* conf, long long n, float* scratch256, float* out, cudaStream_t st) {
+  if (n <= 0) { set_error("conf_score: empty input"); return -1; }
+  launch_pdl(conf_partial_kernel, dim3(256), dim3(256), 0, st, conf, n, scratch256);
+  launch_pdl(conf_final_kernel, dim3(1), dim3(256), 0, st, (const float*)scratch256, 256, n, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
 }  // namespace s3r

@@ -9,6 +9,7 @@ The modules below hold parameters only.  All arithmetic runs in libspann3r_b200.
 `engine.Engine`; there is no eager-PyTorch, CPU or Triton path -- on a machine without an sm_100
 GPU `forward` raises.  Inference (eval mode) only: the training-mode branches of the reference
 (memory dropout, attn_thresh=0, autograd) are out of scope this round.
+`offline_reconstruction` is built on the same engine stages.
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import synth
+from ._lib import conf_score as _conf_score
 from .engine import Engine, MemoryBank, PackedWeights
 
 
@@ -338,5 +340,84 @@ class Spann3R(ParamModule):
             return preds, preds_all, sp_mem
         return preds, preds_all
 
+    # -- offline mode ------------------------------------------------------------
+    def find_initial_pair(self, graph, n_frames):
+        """spann3r/model.py:333-357: the pair with the highest summed confidence score in the pairwise graph
+        (`graph` = output of the reference's dust3r.inference.inference run on `model.dust3r`)."""
+        view1, view2, pred1, pred2 = graph["view1"], graph["view2"], graph["pred1"], graph["pred2"]
+        conf_matrix = torch.zeros(n_frames, n_frames)
+        for i in range(len(view1["idx"])):
+            c1, c2 = pred1["conf"][i].float(), pred2["conf"][i].float()
+            if c1.is_cuda:
+                sc = float(_conf_score(c1.contiguous())) + float(_conf_score(c2.contiguous()))
+            else:   # the reference moves the graph to the CPU (dust3r/inference.py:73): tiny host-side reductions
+                sc = float(((c1 - 1) / c1).mean() + ((c2 - 1) / c2).mean())
+            conf_matrix[int(view1["idx"][i]), int(view2["idx"][i])] = sc
+        flat = int(conf_matrix.argmax())
+        pair_idx = (flat // n_frames, flat % n_frames)
+        print(f"init pair:{pair_idx}, conf: {conf_matrix.max()}")
+        return pair_idx
+
+    @torch.no_grad()
     def offline_reconstruction(self, frames, graph):
-        raise NotImplementedError("offline_reconstruction (spann3r/model.py:394-471) is a SURVEY.md §8f 'next' row")
+        """spann3r/model.py:394-471 + find_next_best_view :359-392 (eval mode).  Every frame is encoded once up front
+        (the reference re-encodes each candidate on every iteration; the features are identical)."""
+        if self.training:
+            raise NotImplementedError("spann3r_b200 implements the inference path; call .eval() first")
+        n_frames = len(frames)
+        idx_todo = list(range(n_frames))
+        B, _, H, W = frames[0]["img"].shape
+        eng = self._engine_for(B, H, W, n_frames=n_frames)
+        N = eng.N
+        sp_mem = SpatialMemory(engine=eng)
+        p0, p1 = self.find_initial_pair(graph, n_frames)
+        idx_used = [p0, p1]
+        idx_todo.remove(p0)
+        idx_todo.remove(p1)
+        imgs = [self._dev(f["img"]) for f in frames]
+        feats = []
+        chunk = max(1, eng.max_images // B)
+        for s in range(0, n_frames, chunk):
+            part = imgs[s: s + chunk]
+            out = eng.encode(torch.cat(part, dim=0) if len(part) > 1 else part[0])
+            feats += list(out.view(len(part), B, N, 1024).unbind(0))
+
+        def decode_heads(f_fuse, f2):
+            eng.decode(f_fuse, f2)
+            pts, conf = eng.heads()
+            return ({"pts3d": pts[0], "conf": conf[0]}, {"pts3d": pts[1], "conf": conf[1]})
+
+        feat1, feat2 = feats[p0], feats[p1]
+        feat_fuse = feat1
+        res1, res2 = decode_heads(feat_fuse, feat2)
+        feat_k2, preds, preds_all = None, None, []
+        while True:
+            if feat_k2 is not None:
+                feat1 = feat2
+                feat_fuse = sp_mem.memory_read(feat_k2, res=True)
+                best_conf, best_id = 0.0, None
+                for i in idx_todo:                                   # find_next_best_view
+                    r1, r2 = decode_heads(feat_fuse, feats[i])
+                    total = float(_conf_score(r1["conf"].contiguous())) + float(_conf_score(r2["conf"].contiguous()))
+                    if total > best_conf:
+                        best_conf, best_id = total, i
+                idx_todo.remove(best_id)
+                idx_used.append(best_id)
+                print(f"next best view: {best_id}, conf: {best_conf}")
+                feat2 = feats[best_id]
+                res1, res2 = decode_heads(feat_fuse, feat2)          # restores the engine's hooks for the winner
+            feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
+            mem_v = eng.value(res1["pts3d"], feat_k1)
+            sp_mem.add_mem_check(feat_k1, mem_v)
+            res2["pts3d_in_other_view"] = res2.pop("pts3d")
+            if preds is None:
+                preds = [res1]
+                preds_all = [(res1, res2)]
+            else:
+                res1["pts3d_in_other_view"] = res1.pop("pts3d")
+                preds.append(res1)
+                preds_all.append((res1, res2))
+            if len(idx_todo) == 0:
+                break
+        preds.append(res2)
+        return preds, preds_all, idx_used

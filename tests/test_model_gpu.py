@@ -213,3 +213,31 @@ def test_config4_100_frames_512x384_bank_stress(models):
             worst = max(worst, rel_l2(p[k].cpu(), r[k].cpu()))
     print("config 4 worst rel-L2 over 100 frames: %.2e" % worst)
     assert worst < 1e-3
+
+
+def test_offline_reconstruction_matches_reference_golden(models):
+    """SURVEY.md §8f rank 2 on the CUDA path: pairwise graph through `model.dust3r(view1, view2)`, then
+    `offline_reconstruction` -- same visiting order and (<= 1e-3) same predictions as the real reference."""
+    import contextlib
+    import io
+    from spann3r_b200 import synth
+    from test_oracle_vs_golden import _pair_graph
+    g = np.load(os.path.join(GOLDEN, "offline_224_4f_sharp.npz"))
+    m = models[True]
+    frames = synth.make_frames(4, 224, 224)
+
+    def fwd(a, b):
+        r1, r2 = m.dust3r(a, b)
+        return {k: v.clone() for k, v in r1.items()}, {k: v.clone() for k, v in r2.items()}
+
+    graph = _pair_graph(fwd, frames)
+    with contextlib.redirect_stdout(io.StringIO()):
+        preds, preds_all, idx_used = m.offline_reconstruction(frames, graph)
+    assert list(idx_used) == list(g["idx_used"])
+    errs = {}
+    for i, p in enumerate(preds):
+        assert set(p.keys()) == {k.split("/")[-1] for k in g.files if k.startswith(f"preds/{i}/")}
+        for k, v in p.items():
+            errs[f"{i}/{k}"] = rel_l2(v.cpu(), g[f"preds/{i}/{k}"])
+    print({k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs

@@ -85,3 +85,36 @@ def test_rope_matches_curope_formula():
             exp[..., half * 2 * Q + q] = u * c - v * s
             exp[..., half * 2 * Q + q + Q] = v * c + u * s
     assert rel_l2(out, exp) < 1e-6
+
+
+def _pair_graph(forward_fn, frames):
+    """The pairwise graph `dust3r.inference.inference` builds for a complete scene graph (every ordered pair once;
+    the reference's symmetrised duplicates carry the same numbers)."""
+    v1i, v2i, c1, c2 = [], [], [], []
+    for a in range(len(frames)):
+        for b in range(len(frames)):
+            if a == b:
+                continue
+            r1, r2 = forward_fn(frames[a], frames[b])
+            v1i.append(a); v2i.append(b); c1.append(r1["conf"].cpu()); c2.append(r2["conf"].cpu())
+    return {"view1": {"idx": v1i}, "view2": {"idx": v2i}, "pred1": {"conf": torch.cat(c1)}, "pred2": {"conf": torch.cat(c2)}}
+
+
+def test_offline_reconstruction_matches_reference():
+    """make_pairs -> inference -> Spann3R.offline_reconstruction of the REAL reference
+    (tools/make_golden.py:run_offline) vs the oracle's restatement."""
+    g = np.load(os.path.join(GOLDEN, "offline_224_4f_sharp.npz"))
+    sd = get_state_dict(True)
+    frames = synth.make_frames(4, 224, 224)
+    graph = _pair_graph(lambda a, b: orc.dust3r_forward(sd, a, b), frames)
+    # the pairwise confidences agree with the reference's inference() output
+    for i in range(len(g["graph/view1_idx"])):
+        a, b = int(g["graph/view1_idx"][i]), int(g["graph/view2_idx"][i])
+        j = [k for k in range(len(graph["view1"]["idx"])) if graph["view1"]["idx"][k] == a and graph["view2"]["idx"][k] == b][0]
+        assert rel_l2(graph["pred1"]["conf"][j][::4, ::4], g["graph/pred1_conf"][i]) < TOL
+        assert rel_l2(graph["pred2"]["conf"][j][::4, ::4], g["graph/pred2_conf"][i]) < TOL
+    preds, preds_all, idx_used = orc.offline_reconstruction(sd, frames, graph)
+    assert list(idx_used) == list(g["idx_used"])
+    for i, p in enumerate(preds):
+        for k, v in p.items():
+            assert rel_l2(v, g[f"preds/{i}/{k}"]) < TOL, (i, k)

@@ -13,6 +13,7 @@ Outputs
   tests/golden/cfg1_224_2f_raw.npz    BASELINE config 1 (2 x 224x224), raw random-init weights
   tests/golden/seq_224_4f_sharp.npz   4 x 224x224, sharpened weights (two memory reads)
   tests/golden/seq_384x512_3f_sharp.npz  3 x 384x512, sharpened, outputs sub-sampled (::4, ::4)
+  tests/golden/offline_224_4f_sharp.npz  offline mode: 4 x 224x224, complete pair graph -> offline_reconstruction
 Each npz also holds sub-sampled per-stage activations captured with forward hooks so that a
 parity failure can be localised to a stage.
 """
@@ -134,6 +135,30 @@ def run(model, frames, out_path, px_stride=1, hooks=True):
           f"{os.path.getsize(out_path)/1e6:.2f} MB")
 
 
+def run_offline(model, frames, out_path):
+    """demo.py:104-118 offline branch: make_pairs (complete, symmetrized) -> dust3r.inference.inference -> offline_reconstruction."""
+    from dust3r.image_pairs import make_pairs  # noqa (reference)
+    from dust3r.inference import inference  # noqa (reference)
+    imgs_all = [dict(img=f["img"], true_shape=torch.tensor(f["img"].shape[2:]).unsqueeze(0), idx=j, instance=str(j))
+                for j, f in enumerate(frames)]
+    pairs = make_pairs(imgs_all, scene_graph="complete", prefilter=None, symmetrize=True)
+    t0 = time.time()
+    with torch.no_grad():
+        output = inference(pairs, model.dust3r, "cpu", batch_size=2, verbose=False)
+        preds, preds_all, idx_used = model.offline_reconstruction(frames, output)
+    out = {"idx_used": np.array(idx_used), "graph/view1_idx": np.array(output["view1"]["idx"]),
+           "graph/view2_idx": np.array(output["view2"]["idx"]),
+           "graph/pred1_conf": output["pred1"]["conf"][:, ::4, ::4].contiguous().numpy(),
+           "graph/pred2_conf": output["pred2"]["conf"][:, ::4, ::4].contiguous().numpy(),
+           "graph/pred1_pts3d": output["pred1"]["pts3d"][:, ::4, ::4].contiguous().numpy(),
+           "meta/ref_seconds": np.array(time.time() - t0)}
+    for i, p in enumerate(preds):
+        for k, v in p.items():
+            out[f"preds/{i}/{k}"] = v.contiguous().numpy()
+    np.savez_compressed(out_path, **out)
+    print(f"wrote {out_path}: idx_used={idx_used}, {time.time() - t0:.1f}s, {os.path.getsize(out_path)/1e6:.2f} MB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -146,8 +171,10 @@ def main():
         if args.only != "spec":
             run(m, synth.make_frames(2, 224, 224), os.path.join(GOLD, "cfg1_224_2f_raw.npz"))
         del m
-    if args.only in ("all", "seq224", "seq512"):
+    if args.only in ("all", "seq224", "seq512", "offline"):
         m = build_reference(sharpen=True)
+        if args.only in ("all", "offline"):
+            run_offline(m, synth.make_frames(4, 224, 224), os.path.join(GOLD, "offline_224_4f_sharp.npz"))
         if args.only in ("all", "seq224"):
             run(m, synth.make_frames(4, 224, 224), os.path.join(GOLD, "seq_224_4f_sharp.npz"))
         if args.only in ("all", "seq512"):
