@@ -233,12 +233,14 @@ int launch_im2col_3x3s2(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, int 
 // follows ATen's upsample_bilinear2d (scale = (in-1)/(out-1); src = scale*dst; lambda1 = src - floor).
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const float* __restrict__ x, int NB, int H, int W, int C, float* __restrict__ out,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Ho, int Wo) {
   pdl_launch_dependents();
   pdl_wait();
-  const int Ho = 2 * H, Wo = 2 * W, c4 = C >> 2;
-  const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
-  const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  // (Ho, Wo) <= (2H, 2W): the output may be cropped (dust3r/heads/dpt_head.py:56 crops refinenet4's output to the next
+  // level's size when the patch grid is odd); the interpolation grid is always that of the full 2H x 2W image
+  const int c4 = C >> 2;
+  const float sh = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
+  const float sw = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
   const long long total = (long long)NB * Ho * Wo * c4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -273,13 +275,16 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int NB, int H, in
 }
 
 int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, __nv_bfloat16* hi, __nv_bfloat16* lo,
-                      cudaStream_t st) {
+                      cudaStream_t st, int Ho, int Wo) {
   if (C % 4) { set_error("upsample2x: C %% 4 != 0"); return -1; }
-  const long long total = (long long)NB * 4 * H * W * (C / 4);
+  if (Ho <= 0) Ho = 2 * H;
+  if (Wo <= 0) Wo = 2 * W;
+  if (Ho > 2 * H || Wo > 2 * W) { set_error("upsample2x: output %dx%d larger than 2x input", Ho, Wo); return -1; }
+  const long long total = (long long)NB * Ho * Wo * (C / 4);
   if (total == 0) return 0;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  launch_pdl(upsample2x_kernel, dim3((int)blocks), dim3(256), 0, st, x, NB, H, W, C, out, hi, lo);
+  launch_pdl(upsample2x_kernel, dim3((int)blocks), dim3(256), 0, st, x, NB, H, W, C, out, hi, lo, Ho, Wo);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -111,7 +112,9 @@ struct s3r_engine {
 
   std::map<int, PlanCache> pc_encode;  // keyed by nimg
   PlanCache pc_decode, pc_keys, pc_heads, pc_value;
-  std::map<std::pair<long long, const void*>, PlanCache> pc_memread;  // keyed by (len, bank)
+  // keyed by everything the cached tensor maps bake in: bank length, capacity and BOTH plane base pointers (a new
+  // MemoryBank may reuse one address but not the other)
+  std::map<std::tuple<long long, long long, const void*, const void*, const void*, const void*>, PlanCache> pc_memread;
 
   template <typename T>
   T* alloc(size_t n) {
@@ -252,8 +255,8 @@ static __global__ void bank_bump_kernel(float* count, float* attn, long long ld,
 extern "C" {
 
 s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int width, int max_images) {
-  if (!w || batch <= 0 || height % 32 != 0 || width % 32 != 0 || height <= 0 || width <= 0) {
-    set_error("s3r_engine_create: need batch > 0 and height, width multiples of 32 (got %d, %dx%d)", batch, height, width);
+  if (!w || batch <= 0 || height % 16 != 0 || width % 16 != 0 || height <= 0 || width <= 0) {
+    set_error("s3r_engine_create: need batch > 0 and height, width multiples of 16 (got %d, %dx%d)", batch, height, width);
     return nullptr;
   }
   if (max_images < 2 * batch) max_images = 2 * batch;
@@ -605,11 +608,8 @@ int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
     { Epi ep; ep.out = e->Rlow; ep.ldo = 256; if ((r = conv1x1(e->Rb, Hh, Ww, 256, f.out_conv, 256, ep))) return r; }
     ++e->launches;
     if (lvl > 0) {
-      if (2 * Hh != LH[lvl - 1] || 2 * Ww != LW[lvl - 1]) {
-        set_error("s3r_engine_heads: odd patch grid %dx%d is not supported by the DPT pyramid", gh, gw);
-        return -1;
-      }
-      if ((r = launch_upsample2x(e->Rlow, 2 * B, Hh, Ww, 256, e->Rpath, nullptr, nullptr, st))) return r;
+      // refinenet4's output is cropped to layers[2]'s size when the patch grid is odd (dpt_head.py:56)
+      if ((r = launch_upsample2x(e->Rlow, 2 * B, Hh, Ww, 256, e->Rpath, nullptr, nullptr, st, LH[lvl - 1], LW[lvl - 1]))) return r;
       path = e->Rpath;
     } else {
       if ((r = launch_upsample2x(e->Rlow, 2 * B, Hh, Ww, 256, nullptr, e->P1.hi, e->P1.lo, st))) return r;
@@ -676,7 +676,8 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
     e->mem_cap = cap;
     e->pc_memread.clear();
   }
-  PlanCache& pc = e->pc_memread[std::make_pair((long long)M, (const void*)bank->kn_hi)];
+  PlanCache& pc = e->pc_memread[std::make_tuple((long long)M, (long long)cap, (const void*)bank->kn_hi, (const void*)bank->kn_lo,
+                                                (const void*)bank->vnt_hi, (const void*)bank->vnt_lo)];
   pc.begin();
   const long long R = (long long)B * N;
   const int Mpad = (M + 7) / 8 * 8;

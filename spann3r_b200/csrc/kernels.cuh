@@ -18,8 +18,9 @@ int launch_im2col_patch16(const float* img, long long sb, long long sc, long lon
                           int gw, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 int launch_im2col_3x3s2(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, int NB, int H, int W, int C, int Ho, int Wo,
                         __nv_bfloat16* ohi, __nv_bfloat16* olo, cudaStream_t st);
+// (Ho, Wo) = output size, <= (2H, 2W) (cropped), 0 = exactly 2x
 int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, __nv_bfloat16* hi, __nv_bfloat16* lo,
-                      cudaStream_t st);
+                      cudaStream_t st, int Ho = 0, int Wo = 0);
 int launch_rope2d(float* tokens, const long long* pos, long long BN, int H, int D, long long stride_tok,
                   long long stride_head, float base, float fwd, cudaStream_t st);
 

@@ -241,3 +241,24 @@ def test_offline_reconstruction_matches_reference_golden(models):
             errs[f"{i}/{k}"] = rel_l2(v.cpu(), g[f"preds/{i}/{k}"])
     print({k: "%.1e" % v for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize("H,W", [(336, 512), (288, 512), (160, 512)])
+def test_other_dust3r_resolutions_vs_oracle(models, H, W):
+    """The other aspect ratios DUSt3R is run at; 512x336 has an ODD patch grid (21x32), which exercises the cropped
+    refinenet4 upsample of dust3r/heads/dpt_head.py:56."""
+    from oracle import spann3r_oracle as orc
+    from spann3r_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = models[True]
+    sd = {k: v.cuda() for k, v in get_state_dict(True).items()}
+    frames = synth.make_frames(3, H, W)
+    preds, _ = m(frames)
+    keep = [{k: v.clone() for k, v in p.items()} for p in preds]
+    ref, _ = orc.forward(sd, [{"img": f["img"].cuda()} for f in frames])
+    for p, r in zip(keep, ref):
+        assert set(p) == set(r)
+        for k in r:
+            assert p[k].shape == r[k].shape
+            assert rel_l2(p[k].cpu(), r[k].cpu()) < TOL, (H, W, k)
