@@ -29,6 +29,8 @@ enum { S3R_EPI_PLAIN = 0, S3R_EPI_PIXSHUF = 1, S3R_EPI_QKV = 2, S3R_EPI_HEADTAIL
 enum { S3R_ACT_NONE = 0, S3R_ACT_GELU = 1, S3R_ACT_RELU = 2 };
 
 int s3r_version(void);
+/* sizeof(s3r_gemm_desc / s3r_model_w / s3r_bank) as compiled: bindings check their mirrors against these */
+int s3r_abi_sizeof(int which /* 0 gemm_desc, 1 model_w, 2 bank */);
 /* last error text of the calling thread ("" if none) */
 const char* s3r_last_error(void);
 /* 1 if a CUDA device of compute capability 10.x is visible, else 0 (never falls back to CPU) */
@@ -97,6 +99,15 @@ typedef struct s3r_gemm_desc {
    * postprocess: pts3d = xyz/|xyz| * expm1(|xyz|), conf = 1 + exp(x3).
    * croco/models/dpt_block.py:318-324, dust3r/heads/postprocess.py:10-58. */
   const float* ht_w; const float* ht_b; float* ht_pts; float* ht_conf;
+  /* Folded LayerNorm (croco/models/blocks.py:127-130,186-191: every Linear that follows a LayerNorm).  Consumer:
+   * A = planes of the RAW residual stream x, B = planes of W diag(gamma), bias = b + W beta, ln_cs [groups*n] = row
+   * sums of the B planes (hi + lo), ln_stats [A rows, ln_np] float2 (sum, sum of squares) per 32-column chunk of x
+   * (ln_np = kc/32); the epilogue applies rstd_r * (acc - mean_r * ln_cs[col]) + bias = LN(x) W^T + b.
+   * a_swap = 1: group g reads A rows / statistics of group groups-1-g (norm_y of the twin decoders,
+   * dust3r/model.py:197-199).  Producer (EPI_PLAIN, n % 32 == 0): stats_out [rows, n/32] float2 receives the chunk
+   * sums of the rows it writes.  All NULL / 0 = plain GEMM. */
+  const float* ln_stats; int ln_np; float ln_eps; const float* ln_cs; int a_swap;
+  float* stats_out;
 } s3r_gemm_desc;
 int s3r_gemm(const s3r_gemm_desc* d, void* stream);
 /* tile width the planner would pick (64/128/256), for tests */
@@ -122,7 +133,9 @@ int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, 
  * and the two DPT heads (downstream_head1/2). */
 typedef struct s3r_planes { const void* hi; const void* lo; } s3r_planes;
 typedef struct s3r_ln { const float* w; const float* b; } s3r_ln;      /* grouped: [G, C] contiguous */
-typedef struct s3r_lin { s3r_planes w; const float* b; } s3r_lin;      /* b may be NULL */
+/* b may be NULL.  cs != NULL marks a LayerNorm-folded linear: w = planes of W diag(gamma), b = b + W beta,
+ * cs [G*N] = row sums of the planes (see s3r_gemm_desc.ln_cs); the preceding s3r_ln is then unused by the engine. */
+typedef struct s3r_lin { s3r_planes w; const float* b; const float* cs; } s3r_lin;
 
 typedef struct s3r_block_w {       /* croco/models/blocks.py:114-130 */
   s3r_ln norm1; s3r_lin qkv; s3r_lin proj; s3r_ln norm2; s3r_lin fc1; s3r_lin fc2;

@@ -34,11 +34,14 @@ class GemmDesc(C.Structure):
         ("q_pos", _vp), ("q_cs", _vp),
         ("q_out", _vp), ("k_out", _vp), ("vt_out", _vp), ("q_scale", _f),
         ("ht_w", _vp), ("ht_b", _vp), ("ht_pts", _vp), ("ht_conf", _vp),
+        ("ln_stats", _vp), ("ln_np", _i), ("ln_eps", _f), ("ln_cs", _vp), ("a_swap", _i),
+        ("stats_out", _vp),
     ]
 
 
 _PROTOS = {
     "s3r_version": (_i, []),
+    "s3r_abi_sizeof": (_i, [_i]),
     "s3r_last_error": (C.c_char_p, []),
     "s3r_device_ok": (_i, []),
     "s3r_split": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i64, _i, _i, _vp]),

@@ -15,6 +15,14 @@ static inline const __nv_bfloat16* B(const void* p) { return reinterpret_cast<co
 extern "C" {
 
 int s3r_version(void) { return S3R_VERSION; }
+int s3r_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(s3r_gemm_desc);
+    case 1: return (int)sizeof(s3r_model_w);
+    case 2: return (int)sizeof(s3r_bank);
+  }
+  return -1;
+}
 const char* s3r_last_error(void) { return s3r::last_error(); }
 
 int s3r_device_ok(void) {
@@ -97,6 +105,21 @@ static int fill_plan(const s3r_gemm_desc* d, GemmPlan* plan) {
   }
   if (d->epi == S3R_EPI_HEADTAIL) {
     a.ht_w = d->ht_w; a.ht_b = d->ht_b; a.ht_pts = d->ht_pts; a.ht_conf = d->ht_conf;
+  }
+  if (d->ln_stats) {
+    if (d->ln_cs == nullptr || d->ln_np * 32 != d->kc || d->taps != 1 || d->epi == S3R_EPI_PIXSHUF) {
+      set_error("s3r_gemm: folded LayerNorm needs ln_cs, ln_np == kc/32, taps == 1 and a non-PIXSHUF epilogue");
+      return -1;
+    }
+    a.ln_stats = reinterpret_cast<const float2*>(d->ln_stats); a.ln_np = d->ln_np; a.ln_eps = d->ln_eps; a.ln_cs = d->ln_cs;
+  }
+  a.a_swap = d->a_swap ? 1 : 0;
+  if (d->stats_out) {
+    if (d->epi != S3R_EPI_PLAIN || d->n % 32 != 0) {
+      set_error("s3r_gemm: stats_out needs EPI_PLAIN and n %% 32 == 0");
+      return -1;
+    }
+    a.stats_out = reinterpret_cast<float2*>(d->stats_out);
   }
   return 0;
 }

@@ -49,6 +49,9 @@ struct Epi {
   const int* q_pos = nullptr; const float2* q_cs = nullptr;
   float *q_out = nullptr, *k_out = nullptr, *vt_out = nullptr; float q_scale = 1.f;
   const float *ht_w = nullptr, *ht_b = nullptr; float *ht_pts = nullptr, *ht_conf = nullptr;
+  // folded LayerNorm: consumer side (statistics of the A rows + column sums of the gamma-folded weights) ...
+  const float2* ln_stats = nullptr; int ln_np = 0; float ln_eps = 0.f; const float* ln_cs = nullptr; int a_swap = 0;
+  float2* stats_out = nullptr;   // ... and producer side (chunk sums of the rows this GEMM writes)
 };
 
 // Plans are created on the first pass through a stage and replayed afterwards (same call order).
@@ -96,9 +99,11 @@ struct s3r_engine {
   // lookup tables
   int* pos = nullptr;  // [max_rows, 2] (y, x)
   // encoder / value-encoder workspace (rows up to max_images*N, dim 1024)
-  float* X = nullptr; Planes P, Pim, AO, Hb; float *Qb = nullptr, *Kb = nullptr, *Vtb = nullptr;
+  float* X = nullptr; Planes P, P2, Pim, AO, Hb; float *Qb = nullptr, *Kb = nullptr, *Vtb = nullptr;
+  float2 *St1 = nullptr, *St2 = nullptr;   // LayerNorm chunk statistics of the residual stream (block input / after attention)
   // decoder workspace (2 groups x R rows, dim 768)
-  float* Xd = nullptr; Planes Pa, Pb, AOd, Hd, E0, Hk6, Hk9, Hk12, KH, KHh; float *Qd = nullptr, *Kd = nullptr, *Vtd = nullptr;
+  float2 *Sa = nullptr, *Sb = nullptr, *Sc = nullptr;
+  float* Xd = nullptr; Planes Pa, Pb, Pc, AOd, Hd, E0, Hk6, Hk9, Hk12, KH, KHh; float *Qd = nullptr, *Kd = nullptr, *Vtd = nullptr;
   float* D12 = nullptr; float* KO = nullptr;
   // DPT workspace
   Planes T1, T2, T4, T4c, A1, A2, A3, A4;       // act_postprocess stages
@@ -160,6 +165,8 @@ struct s3r_engine {
     } else if (e.epi == EPI_HEADTAIL) {
       a.ht_w = e.ht_w; a.ht_b = e.ht_b; a.ht_pts = e.ht_pts; a.ht_conf = e.ht_conf;
     }
+    a.ln_stats = e.ln_stats; a.ln_np = e.ln_np; a.ln_eps = e.ln_eps; a.ln_cs = e.ln_cs; a.a_swap = e.a_swap;
+    a.stats_out = e.stats_out;
     flops += p.flops;
     ++launches;
     if (!profiling) return gemm_launch(p, st);
@@ -202,32 +209,37 @@ struct s3r_engine {
   }
 
   // ---- one ViT block on X [nimg*N, D] (in place).  croco/models/blocks.py:127-130 ----
+  // LayerNorms are folded into the GEMM that consumes them (s3r_lin.cs): on entry P holds the planes of the block
+  // input x and St1 its per-row chunk statistics (written by whichever GEMM produced x); on exit likewise for
+  // the block output.  No LayerNorm kernel runs inside a block.
   int vit_block(PlanCache& pc, const s3r_block_w& bw, int D, int nimg, bool rope, float* Xp, cudaStream_t st) {
     const int rows = nimg * N, heads = D / 64;
     int r;
-    if ((r = ln(Xp, bw.norm1, 0, 0, 1e-6f, rows, D, nullptr, 0, P, D, 0, 0, st))) return r;
     {
       Geom g; g.W = rows; g.Kc = D; g.N = 3 * D;
       Epi e; e.epi = EPI_QKV; e.bias = bw.qkv.b; e.q_C = D; e.q_role_base = 0; e.q_ntok = N; e.q_ntok_pad = Npad;
       e.q_rope = rope ? 1 : 0; e.q_nb = nimg; e.q_pos = pos; e.q_cs = (const float2*)w.rope_cs;
       e.q_out = Qb; e.k_out = Kb; e.vt_out = Vtb; e.q_scale = 0.125f;
+      e.ln_stats = St1; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.qkv.cs;                       // norm1
       if ((r = gemm(pc, P, WP(bw.qkv.w), g, e, st))) return r;
     }
     if ((r = attention(pc, Qb, Kb, Vtb, nimg * heads, heads, N, N, AO, D, st))) return r;
     {
       Geom g; g.W = rows; g.Kc = D; g.N = D;
       Epi e; e.bias = bw.proj.b; e.res1 = Xp; e.ldr1 = D; e.out = Xp; e.ldo = D;
+      e.op = P2; e.ldp = D; e.stats_out = St2;
       if ((r = gemm(pc, AO, WP(bw.proj.w), g, e, st))) return r;
     }
-    if ((r = ln(Xp, bw.norm2, 0, 0, 1e-6f, rows, D, nullptr, 0, P, D, 0, 0, st))) return r;
     {
       Geom g; g.W = rows; g.Kc = D; g.N = 4 * D;
       Epi e; e.bias = bw.fc1.b; e.act = ACT_GELU; e.op = Hb; e.ldp = 4 * D;
-      if ((r = gemm(pc, P, WP(bw.fc1.w), g, e, st))) return r;
+      e.ln_stats = St2; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.fc1.cs;                       // norm2
+      if ((r = gemm(pc, P2, WP(bw.fc1.w), g, e, st))) return r;
     }
     {
       Geom g; g.W = rows; g.Kc = 4 * D; g.N = D;
       Epi e; e.bias = bw.fc2.b; e.res1 = Xp; e.ldr1 = D; e.out = Xp; e.ldo = D;
+      e.op = P; e.ldp = D; e.stats_out = St1;
       if ((r = gemm(pc, Hb, WP(bw.fc2.w), g, e, st))) return r;
     }
     return 0;
@@ -278,6 +290,9 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
   // encoder / value encoder
   e->X = e->alloc<float>(Mx * 1024);
   e->P = e->alloc_planes(Mx * 1024);
+  e->P2 = e->alloc_planes(Mx * 1024);
+  e->St1 = e->alloc<float2>(Mx * 32);
+  e->St2 = e->alloc<float2>(Mx * 32);
   e->Pim = e->alloc_planes(Mx * 768);
   e->AO = e->alloc_planes(Mx * 1024);
   e->Hb = e->alloc_planes(Mx * 4096);
@@ -288,6 +303,10 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
   e->Xd = e->alloc<float>(2 * R * 768);
   e->Pa = e->alloc_planes(2 * R * 768);
   e->Pb = e->alloc_planes(2 * R * 768);
+  e->Pc = e->alloc_planes(2 * R * 768);
+  e->Sa = e->alloc<float2>(2 * R * 24);
+  e->Sb = e->alloc<float2>(2 * R * 24);
+  e->Sc = e->alloc<float2>(2 * R * 24);
   e->AOd = e->alloc_planes(2 * R * 768);
   e->Hd = e->alloc_planes(2 * R * 3072);
   e->E0 = e->alloc_planes(2 * R * 1024);
@@ -409,6 +428,7 @@ int s3r_engine_encode(s3r_engine* e, const float* img, int nimg, float* feat, vo
   {
     Geom g; g.W = rows; g.Kc = 768; g.N = 1024;
     Epi ep; ep.bias = e->w.patch_embed.b; ep.out = e->X; ep.ldo = 1024;
+    ep.op = e->P; ep.ldp = 1024; ep.stats_out = e->St1;   // block 0's folded norm1 reads these
     if ((r = e->gemm(pc, e->Pim, WP(e->w.patch_embed.w), g, ep, st))) return r;
   }
   for (int l = 0; l < 24; ++l)
@@ -437,62 +457,72 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
   {
     Geom g; g.W = (int)(2 * R); g.Kc = 1024; g.N = 768;   // shared weights: one group of 2R rows
     Epi ep; ep.bias = e->w.decoder_embed.b; ep.out = e->Xd; ep.ldo = 768;
+    ep.op = e->Pa; ep.ldp = 768; ep.stats_out = e->Sa;
     if ((r = e->gemm(pc, e->E0, WP(e->w.decoder_embed.w), g, ep, st))) return r;
   }
+  // All four LayerNorms of a DecoderBlock are folded into the GEMMs that consume them (s3r_lin.cs).  `xin` = planes
+  // of the layer input (both streams), Sa its chunk statistics: read by qkv (norm1) and -- with the groups swapped,
+  // each stream cross-attends to the OTHER stream's layer input -- by kv (norm_y).  Pb / Sb: x after self attention
+  // (norm2 -> q), Pc / Sc: x after cross attention (norm3 -> fc1).  fc2 writes the next layer's xin / Sa.
+  Planes xin = e->Pa;
   for (int l = 0; l < 12; ++l) {
     const s3r_decblock_w& bw = e->w.dec[l];
-    // y_ = norm_y(y): y is the OTHER stream's layer input -> normalise before Xd is touched, swapped
-    if ((r = e->ln(e->Xd, bw.norm_y, 768, R, 1e-6f, 2 * R, 768, nullptr, 0, e->Pb, 768, 0, R, st))) return r;
     // self attention
-    if ((r = e->ln(e->Xd, bw.norm1, 768, R, 1e-6f, 2 * R, 768, nullptr, 0, e->Pa, 768, 0, 0, st))) return r;
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 2304;
       Epi ep; ep.epi = EPI_QKV; ep.bias = bw.qkv.b; ep.q_C = 768; ep.q_role_base = 0; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
       ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
       ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.q_scale = 0.125f;
-      if ((r = e->gemm(pc, e->Pa, WP(bw.qkv.w), g, ep, st))) return r;
+      ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.qkv.cs;                      // norm1
+      if ((r = e->gemm(pc, xin, WP(bw.qkv.w), g, ep, st))) return r;
     }
     if ((r = e->attention(pc, e->Qd, e->Kd, e->Vtd, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 768;
       Epi ep; ep.bias = bw.proj.b; ep.res1 = e->Xd; ep.ldr1 = 768; ep.out = e->Xd; ep.ldo = 768;
+      ep.op = e->Pb; ep.ldp = 768; ep.stats_out = e->Sb;
       if ((r = e->gemm(pc, e->AOd, WP(bw.proj.w), g, ep, st))) return r;
     }
-    // cross attention: q from norm2(x), k/v from norm_y(y)
-    if ((r = e->ln(e->Xd, bw.norm2, 768, R, 1e-6f, 2 * R, 768, nullptr, 0, e->Pa, 768, 0, 0, st))) return r;
+    // cross attention: q from norm2(x), k/v from norm_y(y), y = the other stream's layer input
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 768;
       Epi ep; ep.epi = EPI_QKV; ep.bias = bw.q.b; ep.q_C = 768; ep.q_role_base = 0; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
       ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
       ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.q_scale = 0.125f;
-      if ((r = e->gemm(pc, e->Pa, WP(bw.q.w), g, ep, st))) return r;
+      ep.ln_stats = e->Sb; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.q.cs;                        // norm2
+      if ((r = e->gemm(pc, e->Pb, WP(bw.q.w), g, ep, st))) return r;
     }
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 1536;
       Epi ep; ep.epi = EPI_QKV; ep.bias = bw.kv.b; ep.q_C = 768; ep.q_role_base = 1; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
       ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
       ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.q_scale = 0.125f;
-      if ((r = e->gemm(pc, e->Pb, WP(bw.kv.w), g, ep, st))) return r;
+      ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.kv.cs; ep.a_swap = 1;        // norm_y
+      if ((r = e->gemm(pc, xin, WP(bw.kv.w), g, ep, st))) return r;
     }
     if ((r = e->attention(pc, e->Qd, e->Kd, e->Vtd, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 768;
       Epi ep; ep.bias = bw.cproj.b; ep.res1 = e->Xd; ep.ldr1 = 768; ep.out = e->Xd; ep.ldo = 768;
+      ep.op = e->Pc; ep.ldp = 768; ep.stats_out = e->Sc;
       if ((r = e->gemm(pc, e->AOd, WP(bw.cproj.w), g, ep, st))) return r;
     }
     // MLP
-    if ((r = e->ln(e->Xd, bw.norm3, 768, R, 1e-6f, 2 * R, 768, nullptr, 0, e->Pa, 768, 0, 0, st))) return r;
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 3072;
       Epi ep; ep.bias = bw.fc1.b; ep.act = ACT_GELU; ep.op = e->Hd; ep.ldp = 3072;
-      if ((r = e->gemm(pc, e->Pa, WP(bw.fc1.w), g, ep, st))) return r;
+      ep.ln_stats = e->Sc; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.fc1.cs;                      // norm3
+      if ((r = e->gemm(pc, e->Pc, WP(bw.fc1.w), g, ep, st))) return r;
     }
     {
+      // the planes of the layer output are the next layer's xin; after layers 6 and 9 they are also DPT hooks
+      // (dpt_head.py:108), so those layers write them straight into the hook buffers
+      Planes xout = (l == 5) ? e->Hk6 : (l == 8) ? e->Hk9 : e->Pa;
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 3072; g.N = 768;
       Epi ep; ep.bias = bw.fc2.b; ep.res1 = e->Xd; ep.ldr1 = 768; ep.out = e->Xd; ep.ldo = 768;
-      if (l == 5) { ep.op = e->Hk6; ep.ldp = 768; }   // DPT hooks: decoder layers 6 and 9 (dpt_head.py:108)
-      if (l == 8) { ep.op = e->Hk9; ep.ldp = 768; }
+      ep.op = xout; ep.ldp = 768; ep.stats_out = e->Sa;
       if ((r = e->gemm(pc, e->Hd, WP(bw.fc2.w), g, ep, st))) return r;
+      xin = xout;
     }
     if (dec_all && l < 11) {
       ++e->launches;
@@ -644,6 +674,7 @@ int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, fl
   {
     Geom g; g.W = rows; g.Kc = 768; g.N = 1024;
     Epi ep; ep.bias = e->w.pos_patch_embed.b; ep.out = e->Xv; ep.ldo = 1024;
+    ep.op = e->P; ep.ldp = 1024; ep.stats_out = e->St1;
     if ((r = e->gemm(pc, e->Pim, WP(e->w.pos_patch_embed.w), g, ep, st))) return r;
   }
   for (int l = 0; l < 6; ++l)
@@ -693,10 +724,11 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
     Planes Kn; Kn.hi = (__nv_bfloat16*)bank->kn_hi; Kn.lo = (__nv_bfloat16*)bank->kn_lo;
     if ((r = e->gemm(pc, e->Qn, Kn, g, ep, st))) return r;
   }
-  e->launches += 2;
+  e->launches += 3;
   if ((r = launch_mem_softmax(e->Sm, e->mem_cap, R, M, Mpad, 1.0f / 32.0f, thresh, e->Pm.hi, e->Pm.lo, e->mem_cap, st)))
     return r;
-  if ((r = launch_mem_colsum(e->Pm.hi, e->Pm.lo, e->mem_cap, B, N, M, bank->attn, cap, st))) return r;
+  // the fp32 scores are dead once the softmax has run: Sm doubles as the [B, chunks, mem_cap] partial-sum scratch
+  if ((r = launch_mem_colsum(e->Pm.hi, e->Pm.lo, e->mem_cap, B, N, M, bank->attn, cap, e->Sm, e->mem_cap, st))) return r;
   {  // out = attn . LN_v(mem_v) + feat
     Geom g; g.groups = B; g.W = N; g.Kc = M; g.N = 1024; g.lda = e->mem_cap; g.ldb = cap; g.b_group_rows = 1024;
     Epi ep; ep.res1 = feat; ep.ldr1 = 1024; ep.out = out; ep.ldo = 1024;

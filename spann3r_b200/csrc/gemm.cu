@@ -41,7 +41,8 @@ struct GemmCfg {
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = kSmemRing / STAGE;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int COLV = 2 * 2 * BN * 4;  // per accumulator stage: staged bias + LN-fold column sums of the tile
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + COLV;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
 };
 
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* colv = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE + 256);   // [2 stages][bias | colsum][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         const int th = (mt / args.tiles_w) % args.tiles_h;
         const int nb = mt / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.bw, h0 = th * args.bh;
-        const int img = g * args.NB + nb;
+        const int img = (args.a_swap ? (args.groups - 1 - g) : g) * args.NB + nb;
         const int brow = g * args.b_group_rows + nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / args.kpt;
@@ -194,6 +196,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
       const long long pix = ((long long)nb * args.H + h) * args.W + w;  // row inside the group
       const long long grow = (long long)g * args.out_group_rows + pix;  // global output row (PLAIN)
 
+      // everything that does not need the accumulator is requested while the main loop of this tile still runs:
+      // the tile's bias / colsum columns (-> smem), the row's LayerNorm statistics and RoPE position, and the
+      // residual values of the first chunk
+      float* sb = colv + as * 2 * BN;
+      float* scs = sb + BN;
+      epi_stage_cols<EPI, BN>(args, sb, scs, g, nt, (int)threadIdx.x - 64, 128);
+      EpiRow er;
+      epi_row_init<EPI>(args, er, g, pix, grow, valid);
+      float4 rcur[8], rnxt[8];
+      if (nt * BN < args.N) epi_prefetch_res<EPI>(args, rcur, grow, valid, nt * BN);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // staged columns visible to the 4 epilogue warps
+
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
@@ -205,12 +219,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         if (col0 >= args.N) break;  // warp-uniform
         uint32_t raw[32];
         tmem_ld_32x32(tbase + c * 32, raw);
+        if (c + 1 < BN / 32 && col0 + 32 < args.N) epi_prefetch_res<EPI>(args, rnxt, grow, valid, col0 + 32);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-        epi_chunk<EPI>(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+        epi_chunk<EPI>(args, v, sb + c * 32, scs + c * 32, er, rcur, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
       }
       // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before_sync();
@@ -347,7 +364,9 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   // nothing at M=768 where fixed per-kernel costs dominate); g2_mode 128/256 forces them wherever they are legal.
   const long long tiles128 = m_tiles * ((N + 127) / 128);
   const bool legal2 = (m_tiles_group % 2 == 0) && N >= 128;
-  if (force_bn == 0 && legal2 && ((g2_mode == 1 && taps == 1 && tiles128 >= 400) || g2_mode == 128 || g2_mode == 256)) {
+  static const int g2_conv = getenv("S3R_GEMM2_CONV") ? atoi(getenv("S3R_GEMM2_CONV")) : 0;   // 1: also 3x3 convs
+  if (force_bn == 0 && legal2 &&
+      ((g2_mode == 1 && (taps == 1 || g2_conv) && tiles128 >= 400) || g2_mode == 128 || g2_mode == 256)) {
     two = 1;
     bn = (N >= 256 && N % 256 == 0) ? 256 : 128;
     if (g2_mode == 128) bn = 128;

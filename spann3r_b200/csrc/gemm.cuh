@@ -39,6 +39,14 @@ struct GemmArgs {
   float* out_f32; int ldo;            // row stride in elements
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldp; int plane_col0;
   long long out_group_rows;           // rows of `out`/`res`/planes per group
+  // Folded LayerNorm (consumer side): A holds the planes of the RAW residual stream x, the weights carry gamma
+  // (W' = W diag(gamma), bias' = b + W beta), and the epilogue applies rstd_r * (acc - mean_r * ln_cs[col]) + bias'.
+  // ln_stats [A rows, ln_np] = (sum, sum of squares) per 32-column chunk of x, written by the producer's epilogue.
+  const float2* ln_stats; int ln_np; float ln_eps;
+  const float* ln_cs;                 // [G*N] column sums of W' (as the tensor core sees it: hi + lo planes)
+  int a_swap;                         // 1: group g reads the A rows (and statistics) of group G-1-g (norm_y of the twin decoders)
+  // Producer side (EPI_PLAIN): write (sum, sum of squares) of every output row chunk, [rows, N/32]
+  float2* stats_out;
   // EPI_PIXSHUF
   int ps_s, ps_cout;
   // EPI_QKV

@@ -28,7 +28,8 @@ struct Gemm2Cfg {
   static constexpr int B_TILE = (BN / 2) * g2::BK * 2;    // one plane, this CTA's half of the BN rows
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = g2::kSmemRing / STAGE;
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int COLV = 2 * 2 * BN * 4;   // per accumulator stage: staged bias + LN-fold column sums of the tile
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + COLV;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -107,6 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // per CTA, multicast commit from the leader
   uint64_t* tmem_empty = tmem_full + 2;            // used in the leader only (count 2 * kEpiWarps)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* colv = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE + 256);   // [2 stages][bias | colsum][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,7 +162,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         const int th = (mt / args.tiles_w) % args.tiles_h;
         const int nb = mt / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.bw, h0 = th * args.bh;
-        const int img = g * args.NB + nb;
+        const int img = (args.a_swap ? (args.groups - 1 - g) : g) * args.NB + nb;
         const int brow = g * args.b_group_rows + nt * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / args.kpt;
@@ -253,11 +255,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
       const long long pix = ((long long)nb * args.H + h) * args.W + w;
       const long long grow = (long long)g * args.out_group_rows + pix;
 
+      // requested while the main loop of this tile still runs (see gemm.cu): staged bias / colsum columns, the
+      // row's LayerNorm statistics and RoPE position, the first chunk's residual values
+      constexpr int CH = BN / 64;  // 32-column chunks per warp
+      float* sb = colv + as * 2 * BN;
+      float* scs = sb + BN;
+      epi_stage_cols<EPI, BN>(args, sb, scs, g, nt, (int)threadIdx.x - 64, 32 * kEpiWarps);
+      EpiRow er;
+      epi_row_init<EPI>(args, er, g, pix, grow, valid);
+      float4 rcur[8], rnxt[8];
+      const int cfirst = nt * BN + half * CH * 32;
+      if (cfirst < args.N) epi_prefetch_res<EPI>(args, rcur, grow, valid, cfirst);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // staged columns visible to the 8 epilogue warps
+
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
       float ht_acc[4] = {0.f, 0.f, 0.f, 0.f};
-      constexpr int CH = BN / 64;  // 32-column chunks per warp
 #pragma unroll 1
       for (int cc = 0; cc < CH; ++cc) {
         const int c = half * CH + cc;
@@ -265,11 +279,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         if (col0 >= args.N) break;
         uint32_t raw[32];
         tmem_ld_32x32(tbase + c * 32, raw);
+        if (cc + 1 < CH && col0 + 32 < args.N) epi_prefetch_res<EPI>(args, rnxt, grow, valid, col0 + 32);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epi_chunk<EPI>(args, v, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+        epi_chunk<EPI>(args, v, sb + c * 32, scs + c * 32, er, rcur, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
       }
       tc_fence_before_sync();
       __syncwarp();

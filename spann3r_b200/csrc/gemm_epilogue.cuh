@@ -12,25 +12,85 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// v: 32 accumulator values (columns col0 .. col0+31 of group g); (nb, h, w): the row's pixel; pix: row index inside the
-// group; grow: global output row for EPI_PLAIN; ht_acc: running 1x1-conv dot products of EPI_HEADTAIL.
+// Per-tile column vectors staged in shared memory by the epilogue warps BEFORE they wait for the accumulator (the
+// loads overlap the main loop): sb[j] = bias of tile column j (0 when there is none), scs[j] = column sum of the
+// LayerNorm-folded weights (ln_cs, see GemmArgs).  Call with every epilogue thread, then barrier among them.
+template <int EPI, int BN>
+__device__ __forceinline__ void epi_stage_cols(const GemmArgs& args, float* sb, float* scs, int g, int nt, int tid_e,
+                                               int nthr_e) {
+  for (int j = tid_e; j < BN; j += nthr_e) {
+    const int col = nt * BN + j;
+    float b = 0.f, c = 0.f;
+    if (col < args.N) {
+      if (args.bias != nullptr)
+        b = __ldg(args.bias + ((EPI == EPI_PIXSHUF) ? (long long)g * args.ps_cout + (col % args.ps_cout)
+                                                    : (long long)g * args.N + col));
+      if (args.ln_cs != nullptr) c = __ldg(args.ln_cs + (long long)g * args.N + col);
+    }
+    sb[j] = b;
+    scs[j] = c;
+  }
+}
+
+// Per-row state of one tile, loaded before the accumulator wait: LayerNorm statistics of the A row (folded
+// LayerNorm: the GEMM ran on the raw x planes with gamma folded into the weights, the epilogue applies
+// rstd * (acc - mean * colsum) -- identical to LN(x) W^T up to fp32 rounding) and the RoPE position of the row.
+struct EpiRow {
+  float rstd = 1.f, rm = 0.f;   // rm = rstd * mean
+  int py = 0, px = 0;
+};
 template <int EPI>
-__device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], int g, int nb, int h, int w, bool valid,
-                                          long long pix, long long grow, int col0, float (&ht_acc)[4]) {
-  // bias
-  if (args.bias != nullptr) {
-    const int bcol = (EPI == EPI_PIXSHUF) ? (col0 % args.ps_cout) : col0;
-    const int bstride = (EPI == EPI_PIXSHUF) ? args.ps_cout : args.N;
-    const float4* bp = reinterpret_cast<const float4*>(args.bias + (long long)g * bstride + bcol);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = __ldg(bp + q);
-      v[4 * q + 0] += b.x;
-      v[4 * q + 1] += b.y;
-      v[4 * q + 2] += b.z;
-      v[4 * q + 3] += b.w;
+__device__ __forceinline__ void epi_row_init(const GemmArgs& args, EpiRow& er, int g, long long pix, long long grow,
+                                             bool valid) {
+  if (args.ln_stats != nullptr && valid) {
+    const int ga = args.a_swap ? (args.groups - 1 - g) : g;
+    const float2* sp = args.ln_stats + ((long long)ga * args.out_group_rows + pix) * args.ln_np;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < args.ln_np; ++i) {
+      const float2 t = sp[i];
+      s1 += t.x;
+      s2 += t.y;
+    }
+    const float inv_c = 1.0f / (float)(args.ln_np * 32);
+    const float mean = s1 * inv_c;
+    const float var = fmaxf(s2 * inv_c - mean * mean, 0.f);
+    er.rstd = rsqrtf(var + args.ln_eps);
+    er.rm = er.rstd * mean;
+  }
+  if constexpr (EPI == EPI_QKV) {
+    if (args.q_rope && valid) {
+      er.py = args.q_pos[grow * 2];
+      er.px = args.q_pos[grow * 2 + 1];
     }
   }
+}
+
+// Residual rows of the NEXT 32-column chunk, requested while the current chunk is processed (EPI_PLAIN only).
+template <int EPI>
+__device__ __forceinline__ void epi_prefetch_res(const GemmArgs& args, float4 (&rp)[8], long long grow, bool valid,
+                                                 int col0) {
+  if constexpr (EPI == EPI_PLAIN) {
+    if (args.res1 != nullptr && valid) {
+      const float4* p = reinterpret_cast<const float4*>(args.res1 + grow * args.ldr1 + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rp[q] = p[q];
+    }
+  }
+}
+
+// v: 32 accumulator values (columns col0 .. col0+31 of group g); (nb, h, w): the row's pixel; pix: row index inside the
+// group; grow: global output row for EPI_PLAIN; sb / scs: this chunk's 32 staged bias / colsum values (shared memory);
+// rp: the prefetched res1 values of this chunk (EPI_PLAIN); ht_acc: running 1x1-conv dot products of EPI_HEADTAIL.
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], const float* sb, const float* scs,
+                                          const EpiRow& er, const float4 (&rp)[8], int g, int nb, int h, int w,
+                                          bool valid, long long pix, long long grow, int col0, float (&ht_acc)[4]) {
+  if (args.ln_stats != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(er.rstd, v[j], -er.rm * scs[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] += sb[j];
   if (args.act != ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], args.act);
@@ -49,25 +109,46 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
     }
     if (valid) {
       if (args.res1 != nullptr) {
-        const float4* rp = reinterpret_cast<const float4*>(args.res1 + orow * args.ldr1 + ocol);
+        if constexpr (EPI == EPI_PLAIN) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[4 * q + 0] += rp[q].x;
+            v[4 * q + 1] += rp[q].y;
+            v[4 * q + 2] += rp[q].z;
+            v[4 * q + 3] += rp[q].w;
+          }
+        } else {
+          const float4* r1 = reinterpret_cast<const float4*>(args.res1 + orow * args.ldr1 + ocol);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = r1[q];
+            v[4 * q + 0] += t.x;
+            v[4 * q + 1] += t.y;
+            v[4 * q + 2] += t.z;
+            v[4 * q + 3] += t.w;
+          }
+        }
+      }
+      if (args.res2 != nullptr) {
+        const float4* r2 = reinterpret_cast<const float4*>(args.res2 + orow * args.ldr2 + ocol);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 t = rp[q];
+          const float4 t = r2[q];
           v[4 * q + 0] += t.x;
           v[4 * q + 1] += t.y;
           v[4 * q + 2] += t.z;
           v[4 * q + 3] += t.w;
         }
       }
-      if (args.res2 != nullptr) {
-        const float4* rp = reinterpret_cast<const float4*>(args.res2 + orow * args.ldr2 + ocol);
+      if constexpr (EPI == EPI_PLAIN) {
+        if (args.stats_out != nullptr) {   // (sum, sum of squares) of this row over the chunk: LayerNorm statistics
+          float s1 = 0.f, s2 = 0.f;         // of the residual stream for the NEXT GEMM's folded LayerNorm
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = rp[q];
-          v[4 * q + 0] += t.x;
-          v[4 * q + 1] += t.y;
-          v[4 * q + 2] += t.z;
-          v[4 * q + 3] += t.w;
+          for (int j = 0; j < 32; ++j) {
+            s1 += v[j];
+            s2 = fmaf(v[j], v[j], s2);
+          }
+          args.stats_out[orow * (long long)(args.N >> 5) + (col0 >> 5)] = make_float2(s1, s2);
         }
       }
       if (args.out_f32 != nullptr) {
@@ -114,7 +195,7 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
     const long long gb = (long long)g * args.q_nb + bidx;
     if (valid) {
       if (role <= 1 && args.q_rope) {
-        const int p = args.q_pos[(grow) * 2 + (d0 >> 5)];
+        const int p = (d0 >> 5) ? er.px : er.py;
         const float2* cs = args.q_cs + p * 16;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

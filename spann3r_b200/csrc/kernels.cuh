@@ -47,8 +47,9 @@ int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, 
 // spatial memory (memory.cu)
 int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int Mpad, float scale, float thresh,
                        __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st);
+// part: scratch of B * ceil(nq/32) rows of ld_part floats (ld_part >= M rounded up to 8)
 int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long long ldP, int B, int nq, int M,
-                      float* mem_attn, long long ld_attn, cudaStream_t st);
+                      float* mem_attn, long long ld_attn, float* part, long long ld_part, cudaStream_t st);
 int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* ohi, __nv_bfloat16* olo, long long ldo,
                            long long out_batch_stride, int col0, cudaStream_t st);
 int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stride, int B, int T, int P, int C,

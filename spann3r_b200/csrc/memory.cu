@@ -98,39 +98,78 @@ int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int
 
 // ------------------------------------------------------------------------------------------------
 // mem_attn[b, m] += sum over the N query rows of attn[b, :, m]   (spann3r/model.py:180-181).
-// One thread per bank column, fixed summation order (deterministic: the prune ranking depends on it).
+// Two fixed-shape passes, fixed summation order (deterministic: the prune ranking depends on it).
+//   pass 1: block = 32 column-octets (256 columns, 16-byte loads of both planes) x 8 row lanes over a chunk of
+//           CS_ROWS rows -> partial[b, chunk, m]     (grid = columns/256 x chunks x B: hundreds of CTAs in flight)
+//   pass 2: mem_attn[b, m] += partial[b, 0, m] + partial[b, 1, m] + ...   in chunk order
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mem_colsum_kernel(const __nv_bfloat16* __restrict__ phi,
-                                                         const __nv_bfloat16* __restrict__ plo, long long ldP, int nq,
-                                                         int M, float* __restrict__ mem_attn, long long ld_attn) {
+constexpr int CS_ROWS = 32;
+__global__ void __launch_bounds__(256) mem_colsum_partial_kernel(const __nv_bfloat16* __restrict__ phi,
+                                                                 const __nv_bfloat16* __restrict__ plo, long long ldP,
+                                                                 int nq, int Mpad, float* __restrict__ part,
+                                                                 long long ld_part) {
   pdl_launch_dependents();
   pdl_wait();
-  // block = 64 columns x 4 row-quarters; each thread sums its quarter of the rows in order, then the 4 partial
-  // sums are combined in a fixed order: deterministic, and 4x more bytes in flight than one thread per column
-  __shared__ float part[4][64];
-  const int cx = threadIdx.x & 63, rq = threadIdx.x >> 6;
-  const int m = blockIdx.x * 64 + cx;
-  const int b = blockIdx.y;
-  const int r0 = (int)(((long long)nq * rq) / 4), r1 = (int)(((long long)nq * (rq + 1)) / 4);
-  float acc = 0.f;
-  if (m < M) {
-    const __nv_bfloat16* ph = phi + (long long)b * nq * ldP + m;
-    const __nv_bfloat16* pl = plo + (long long)b * nq * ldP + m;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) acc += __bfloat162float(ph[r * ldP]) + __bfloat162float(pl[r * ldP]);
+  __shared__ float red[8][256];
+  const int oct = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 256 + oct * 8;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int r0 = chunk * CS_ROWS, r1 = min(nq, r0 + CS_ROWS);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m0 < Mpad) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const long long o = ((long long)b * nq + r) * ldP + m0;
+      const uint4 h = *reinterpret_cast<const uint4*>(phi + o);
+      const uint4 l = *reinterpret_cast<const uint4*>(plo + o);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+      }
+    }
   }
-  part[rq][cx] = acc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][oct * 8 + j] = acc[j];
   __syncthreads();
-  if (rq == 0 && m < M) mem_attn[b * ld_attn + m] += ((part[0][cx] + part[1][cx]) + part[2][cx]) + part[3][cx];
+  const int m = blockIdx.x * 256 + threadIdx.x;
+  if (m < Mpad) {
+    float s = red[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+    part[((long long)b * gridDim.y + chunk) * ld_part + m] = s;
+  }
+}
+__global__ void __launch_bounds__(256) mem_colsum_final_kernel(const float* __restrict__ part, long long ld_part,
+                                                               int chunks, int M, float* __restrict__ mem_attn,
+                                                               long long ld_attn) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (m >= M) return;
+  const float* p = part + (long long)b * chunks * ld_part + m;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += p[c * ld_part];
+  mem_attn[b * ld_attn + m] += s;
 }
 
+// P planes are zero beyond M up to Mpad (mem_softmax_kernel) and ldP, Mpad are multiples of 8 (16-byte loads).
 int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long long ldP, int B, int nq, int M,
-                      float* mem_attn, long long ld_attn, cudaStream_t st) {
+                      float* mem_attn, long long ld_attn, float* part, long long ld_part, cudaStream_t st) {
   if (M == 0) return 0;
-  dim3 grid((M + 63) / 64, B);
-  launch_pdl(mem_colsum_kernel, dim3(grid), dim3(256), 0, st, phi, plo, ldP, nq, M, mem_attn, ld_attn);
+  const int Mpad = (M + 7) / 8 * 8;
+  const int chunks = (nq + CS_ROWS - 1) / CS_ROWS;
+  if (ldP % 8 != 0 || ld_part < Mpad) {
+    set_error("mem_colsum: ldP=%lld must be a multiple of 8 and ld_part=%lld >= %d", ldP, ld_part, Mpad);
+    return -1;
+  }
+  launch_pdl(mem_colsum_partial_kernel, dim3((Mpad + 255) / 256, chunks, B), dim3(256), 0, st, phi, plo, ldP, nq, Mpad,
+             part, ld_part);
+  launch_pdl(mem_colsum_final_kernel, dim3((M + 255) / 256, B), dim3(256), 0, st, (const float*)part, ld_part, chunks, M,
+             mem_attn, ld_attn);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
+int mem_colsum_chunks(int nq) { return (nq + CS_ROWS - 1) / CS_ROWS; }
 
 // ------------------------------------------------------------------------------------------------
 // fp32 x[b, t, c] (t < T, c < C)  ->  split-bf16 planes out[b, c, col0 + t] (row stride ldo): the

@@ -28,7 +28,7 @@ class LN(C.Structure):
 
 
 class Lin(C.Structure):
-    _fields_ = [("w", Planes), ("b", _vp)]
+    _fields_ = [("w", Planes), ("b", _vp), ("cs", _vp)]
 
 
 class BlockW(C.Structure):
@@ -98,6 +98,17 @@ def rope_cs_table(maxpos: int = ROPE_MAXPOS, base: float = 100.0) -> torch.Tenso
     return torch.stack((freqs.cos(), freqs.sin()), dim=-1).contiguous()
 
 
+def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """Fold the affine part of a LayerNorm into the Linear that consumes it (exact algebra, done in fp64):
+
+        LN(x) W^T + b = rstd (x W'^T - mean rowsum(W')) + b',   W' = W diag(gamma),  b' = b + W beta
+
+    so the GEMM can run on the raw residual stream x and its epilogue applies the per-row (mean, rstd)
+    (include/spann3r_b200.h: s3r_gemm_desc.ln_stats / ln_cs).  Returns (W', b') as fp32."""
+    w64, b64 = w.double(), b.double()
+    return (w64 * gamma.double()[None, :]).float(), (b64 + w64 @ beta.double()).float()
+
+
 class PackedWeights:
     """Device-resident packed weights + the `s3r_model_w` pointer table."""
 
@@ -125,6 +136,7 @@ class PackedWeights:
     def _planes(self, w2d: torch.Tensor) -> Planes:
         hi, lo = _lib.split(w2d.contiguous())
         self._keep += [hi, lo]
+        self._last_planes = (hi, lo)
         self.param_bytes += hi.numel() * 4
         p = Planes()
         p.hi, p.lo = hi.data_ptr(), lo.data_ptr()
@@ -147,6 +159,20 @@ class PackedWeights:
     def _linear(self, names) -> Lin:
         return self._lin([self._t(k + ".weight") for k in names], [self._t(k + ".bias") for k in names])
 
+    def _linear_ln(self, names, ln_names) -> Lin:
+        """Linear that follows a LayerNorm, with the LayerNorm folded in (include/spann3r_b200.h, s3r_lin.cs):
+        LN(x) W^T + b = rstd (x W'^T - mean cs) + b'  with  W' = W diag(gamma), b' = b + W beta, cs = rowsum(W').
+        Exact algebra; cs is summed over the split-bf16 planes the tensor core will actually multiply."""
+        ws, bs = [], []
+        for k, ln in zip(names, ln_names):
+            wf, bf = fold_layernorm(self._t(k + ".weight"), self._t(k + ".bias"), self._t(ln + ".weight"), self._t(ln + ".bias"))
+            ws.append(wf)
+            bs.append(bf)
+        l = self._lin(ws, bs)
+        hi, lo = self._last_planes
+        l.cs = self._f32((hi.double() + lo.double()).sum(dim=1).float())
+        return l
+
     def _conv3(self, names, bias=True) -> Lin:   # [Cout, Cin, 3, 3] -> [Cout, tap, Cin]
         ws = [self._t(k + ".weight").permute(0, 2, 3, 1) for k in names]
         return self._lin(ws, [self._t(k + ".bias") for k in names] if bias else None)
@@ -158,10 +184,10 @@ class PackedWeights:
     def _block(self, prefix) -> BlockW:
         b = BlockW()
         b.norm1 = self._ln([prefix + ".norm1"])
-        b.qkv = self._linear([prefix + ".attn.qkv"])
+        b.qkv = self._linear_ln([prefix + ".attn.qkv"], [prefix + ".norm1"])
         b.proj = self._linear([prefix + ".attn.proj"])
         b.norm2 = self._ln([prefix + ".norm2"])
-        b.fc1 = self._linear([prefix + ".mlp.fc1"])
+        b.fc1 = self._linear_ln([prefix + ".mlp.fc1"], [prefix + ".norm2"])
         b.fc2 = self._linear([prefix + ".mlp.fc2"])
         return b
 
@@ -169,19 +195,16 @@ class PackedWeights:
         ps = [f"dust3r.dec_blocks.{l}", f"dust3r.dec_blocks2.{l}"]
         d = DecBlockW()
         d.norm1 = self._ln([p + ".norm1" for p in ps])
-        d.qkv = self._linear([p + ".attn.qkv" for p in ps])
+        d.qkv = self._linear_ln([p + ".attn.qkv" for p in ps], [p + ".norm1" for p in ps])
         d.proj = self._linear([p + ".attn.proj" for p in ps])
         d.norm_y = self._ln([p + ".norm_y" for p in ps])
         d.norm2 = self._ln([p + ".norm2" for p in ps])
-        d.q = self._linear([p + ".cross_attn.projq" for p in ps])
-        kvw, kvb = [], []
-        for p in ps:   # per group: [projk; projv]
-            kvw += [self._t(p + ".cross_attn.projk.weight"), self._t(p + ".cross_attn.projv.weight")]
-            kvb += [self._t(p + ".cross_attn.projk.bias"), self._t(p + ".cross_attn.projv.bias")]
-        d.kv = self._lin(kvw, kvb)
+        d.q = self._linear_ln([p + ".cross_attn.projq" for p in ps], [p + ".norm2" for p in ps])
+        # per group: [projk; projv], both applied to norm_y(y) (croco/models/blocks.py:188-189)
+        d.kv = self._linear_ln([p + f".cross_attn.proj{r}" for p in ps for r in "kv"], [p + ".norm_y" for p in ps for _ in "kv"])
         d.cproj = self._linear([p + ".cross_attn.proj" for p in ps])
         d.norm3 = self._ln([p + ".norm3" for p in ps])
-        d.fc1 = self._linear([p + ".mlp.fc1" for p in ps])
+        d.fc1 = self._linear_ln([p + ".mlp.fc1" for p in ps], [p + ".norm3" for p in ps])
         d.fc2 = self._linear([p + ".mlp.fc2" for p in ps])
         return d
 

@@ -77,3 +77,40 @@ def test_rope_table_matches_reference_fallback():
     cs = rope_cs_table(64)
     cos, sin = rope_tables(32, 64)
     assert torch.equal(cs[..., 0], cos[:, :16]) and torch.equal(cs[..., 1], sin[:, :16])
+
+
+def test_ctypes_mirrors_match_the_compiled_structs():
+    """The ctypes mirrors of s3r_gemm_desc / s3r_model_w / s3r_bank have the sizes the library was compiled with."""
+    from spann3r_b200 import _lib, engine
+    L = _lib.lib()
+    assert L.s3r_abi_sizeof(0) == ctypes.sizeof(_lib.GemmDesc)
+    assert L.s3r_abi_sizeof(1) == ctypes.sizeof(engine.ModelW)
+    assert L.s3r_abi_sizeof(2) == ctypes.sizeof(engine.Bank)
+
+
+def test_layernorm_fold_algebra():
+    """engine.fold_layernorm + the epilogue formula of the folded LayerNorm (gemm_epilogue.cuh: per-row statistics
+    from 32-column chunk sums, rstd * (acc - mean * colsum) + bias') reproduce Linear(LayerNorm(x)) of
+    croco/models/blocks.py:127-130 -- restated here in fp64 / fp32 on the CPU."""
+    from spann3r_b200.engine import fold_layernorm
+    g = torch.Generator().manual_seed(0)
+    C_, N_, R_ = 768, 96, 40
+    x = torch.randn(R_, C_, generator=g) * 3 + 0.7          # non-zero mean: exercises the mean * colsum term
+    w = torch.randn(N_, C_, generator=g) * C_ ** -0.5
+    b = torch.randn(N_, generator=g)
+    gamma = 1 + 0.2 * torch.randn(C_, generator=g)
+    beta = 0.1 * torch.randn(C_, generator=g)
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x.double(), (C_,), gamma.double(), beta.double(), 1e-6),
+                                     w.double(), b.double())
+    wf, bf = fold_layernorm(w, b, gamma, beta)
+    # producer epilogue: (sum, sum of squares) per 32-column chunk, fp32
+    ch = x.view(R_, C_ // 32, 32)
+    s1, s2 = ch.sum(-1), (ch * ch).sum(-1)
+    mean = s1.sum(-1) / C_
+    var = (s2.sum(-1) / C_ - mean * mean).clamp_min(0)
+    rstd = torch.rsqrt(var + 1e-6)
+    acc = x @ wf.t()                                        # the tensor-core GEMM on the raw stream (fp32 here)
+    cs = wf.sum(dim=1)
+    out = rstd[:, None] * acc - (rstd * mean)[:, None] * cs[None, :] + bf[None, :]
+    err = float((out.double() - ref).norm() / ref.norm())
+    assert err < 2e-6, err

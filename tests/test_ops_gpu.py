@@ -65,11 +65,13 @@ def test_linear_bias_gelu_residual(L, rows, K, N, groups, bn):
     assert rel_l2(oh.double() + ol.double(), ref) < TOL_GEMM
 
 
-@pytest.mark.parametrize("NB,H,W,Cin,Cout,groups", [
-    (1, 12, 16, 256, 256, 2), (1, 24, 32, 96, 256, 1), (2, 7, 7, 256, 256, 1), (1, 96, 128, 256, 128, 2),
-    (1, 14, 14, 384, 256, 1), (1, 48, 64, 192, 256, 1), (1, 12, 16, 768, 256, 2),
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,groups,bn", [
+    (1, 12, 16, 256, 256, 2, 0), (1, 24, 32, 96, 256, 1, 0), (2, 7, 7, 256, 256, 1, 0), (1, 96, 128, 256, 128, 2, 0),
+    (1, 14, 14, 384, 256, 1, 0), (1, 48, 64, 192, 256, 1, 0), (1, 12, 16, 768, 256, 2, 0),
+    # 2-CTA pair tiles on a 3x3 conv (two pixel tiles share the weight tile)
+    (1, 96, 128, 256, 256, 2, 2256), (1, 96, 128, 256, 128, 1, 2128), (2, 24, 32, 96, 256, 1, 2256),
 ])
-def test_conv3x3(L, NB, H, W, Cin, Cout, groups):
+def test_conv3x3(L, NB, H, W, Cin, Cout, groups, bn):
     x = _rand(groups * NB, Cin, H, W, seed=6)
     w = _rand(groups * Cout, Cin, 3, 3, seed=7, scale=(9 * Cin) ** -0.5)
     b = _rand(groups * Cout, seed=8, scale=0.1)
@@ -82,7 +84,7 @@ def test_conv3x3(L, NB, H, W, Cin, Cout, groups):
     d = L.GemmDesc()
     d.a_hi, d.a_lo, d.b_hi, d.b_lo = xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr()
     d.groups, d.nb, d.h, d.w, d.kc, d.taps, d.n = groups, NB, H, W, Cin, 9, Cout
-    d.epi, d.act, d.plane_relu = L.EPI_PLAIN, L.ACT_NONE, 1
+    d.epi, d.act, d.plane_relu, d.force_bn = L.EPI_PLAIN, L.ACT_NONE, 1, bn
     d.bias = b.data_ptr()
     d.res1, d.ldr1 = res.data_ptr(), Cout
     d.out_f32, d.ldo = out.data_ptr(), Cout
@@ -261,3 +263,68 @@ def test_layernorm_upsample_im2col_rope(L):
     L.check(L.lib().s3r_rope2d_inplace(L.ptr(tok), L.ptr(pos), 100, 4, 64, 256, 64, 100.0, 1.0, L.stream_ptr()), "rope")
     torch.cuda.synchronize()
     assert rel_l2(tok, exp) < 1e-5
+
+
+@pytest.mark.parametrize("rows,C,N,groups,swap,bn", [
+    (768, 768, 2304, 2, 0, 0), (768, 768, 1536, 2, 1, 0), (768, 1024, 4096, 1, 0, 0), (196, 1024, 3072, 1, 0, 0),
+    (7680, 1024, 3072, 1, 0, 0), (768, 768, 768, 2, 1, 2128), (1000, 768, 768, 1, 0, 64),
+])
+def test_folded_layernorm_chain(L, rows, C, N, groups, swap, bn):
+    """Producer GEMM (x = r + a W0^T + b0: writes x fp32, planes(x) and the per-row chunk statistics) followed by a
+    consumer GEMM with the LayerNorm folded in (engine.fold_layernorm) == Linear(LayerNorm(x)) of
+    croco/models/blocks.py:127-130 / :186-191 (a_swap: norm_y of the other stream, dust3r/model.py:197-199)."""
+    from spann3r_b200.engine import fold_layernorm
+    K0 = 256
+    a = _rand(groups * rows, K0, seed=21)
+    w0 = _rand(C, K0, seed=22, scale=K0 ** -0.5).repeat(groups, 1)
+    b0 = _rand(groups * C, seed=23, scale=0.5) + 0.3
+    r = _rand(groups * rows, C, seed=24, scale=2.0)
+    x = torch.empty(groups * rows, C, device="cuda")
+    xh = torch.empty(x.shape, dtype=torch.bfloat16, device="cuda")
+    xl = torch.empty_like(xh)
+    stats = torch.zeros(groups * rows, C // 32, 2, device="cuda")
+    ap, w0p = L.split(a), L.split(w0.contiguous())
+    d = L.GemmDesc()
+    d.a_hi, d.a_lo, d.b_hi, d.b_lo = ap[0].data_ptr(), ap[1].data_ptr(), w0p[0].data_ptr(), w0p[1].data_ptr()
+    d.groups, d.nb, d.h, d.w, d.kc, d.taps, d.n = groups, 1, 1, rows, K0, 1, C
+    d.epi = L.EPI_PLAIN
+    d.bias = b0.data_ptr()
+    d.res1, d.ldr1 = r.data_ptr(), C
+    d.out_f32, d.ldo = x.data_ptr(), C
+    d.out_hi, d.out_lo, d.ldp = xh.data_ptr(), xl.data_ptr(), C
+    d.stats_out = stats.data_ptr()
+    L.gemm(d)
+    torch.cuda.synchronize()
+    xd = x.double()
+    ch = xd.view(groups * rows, C // 32, 32)
+    assert rel_l2(stats[..., 0], ch.sum(-1)) < 1e-5
+    assert rel_l2(stats[..., 1], (ch * ch).sum(-1)) < 1e-5
+
+    w = _rand(groups * N, C, seed=25, scale=C ** -0.5)
+    b = _rand(groups * N, seed=26, scale=0.1)
+    gamma = 1 + 0.2 * _rand(groups, C, seed=27)
+    beta = 0.1 * _rand(groups, C, seed=28)
+    wf, bf = [], []
+    for g in range(groups):
+        f = fold_layernorm(w[g * N:(g + 1) * N], b[g * N:(g + 1) * N], gamma[g], beta[g])
+        wf.append(f[0]); bf.append(f[1])
+    wf, bf = torch.cat(wf).contiguous(), torch.cat(bf).contiguous()
+    wp = L.split(wf)
+    cs = (wp[0].double() + wp[1].double()).sum(1).float().contiguous()
+    out = torch.empty(groups * rows, N, device="cuda")
+    d2 = L.GemmDesc()
+    d2.a_hi, d2.a_lo, d2.b_hi, d2.b_lo = xh.data_ptr(), xl.data_ptr(), wp[0].data_ptr(), wp[1].data_ptr()
+    d2.groups, d2.nb, d2.h, d2.w, d2.kc, d2.taps, d2.n = groups, 1, 1, rows, C, 1, N
+    d2.epi, d2.force_bn = L.EPI_PLAIN, bn
+    d2.bias = bf.data_ptr()
+    d2.out_f32, d2.ldo = out.data_ptr(), N
+    d2.ln_stats, d2.ln_np, d2.ln_eps, d2.ln_cs, d2.a_swap = stats.data_ptr(), C // 32, 1e-6, cs.data_ptr(), swap
+    L.gemm(d2)
+    torch.cuda.synchronize()
+    xg = xd.view(groups, rows, C)
+    if swap:
+        xg = xg.flip(0)
+    ref = torch.stack([F.linear(F.layer_norm(xg[g], (C,), gamma[g].double(), beta[g].double(), 1e-6),
+                                w[g * N:(g + 1) * N].double(), b[g * N:(g + 1) * N].double()) for g in range(groups)])
+    ref = ref.reshape(groups * rows, N)
+    assert rel_l2(out, ref) < TOL_GEMM, rel_l2(out, ref)
