@@ -108,6 +108,9 @@ typedef struct s3r_gemm_desc {
    * sums of the rows it writes.  All NULL / 0 = plain GEMM. */
   const float* ln_stats; int ln_np; float ln_eps; const float* ln_cs; int a_swap;
   float* stats_out;
+  /* diagnostics: 16 x uint64 %globaltimer stamps of CTA 0 (entry, prologue done, dependency wait done, first operands
+   * landed, accumulator ready, epilogue done, exit, ...; tools/trace_gemm.py); NULL = off.  1-CTA kernel only. */
+  uint64_t* trace;
 } s3r_gemm_desc;
 int s3r_gemm(const s3r_gemm_desc* d, void* stream);
 /* tile width the planner would pick (64/128/256), for tests */
@@ -206,6 +209,9 @@ double s3r_engine_take_flops(s3r_engine* e);
 /* Per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline leg): switch on, run, read.
  * profile_read synchronises the device; out = {gemm_ms, gemm_flops, gemm_launches, attn_ms, attn_flops, attn_launches} */
 void s3r_engine_profile(s3r_engine* e, int on);
+/* per-launch list (in launch order) of the recorded tensor-core launches: duration [ms], algorithmic FLOPs, kind
+ * (0 GEMM / conv, 1 attention); returns the count (call before profile_read, which consumes the records) */
+int s3r_engine_profile_list(s3r_engine* e, double* ms, double* flops, int* kind, int cap);
 int s3r_engine_profile_read(s3r_engine* e, double* out);
 /* number of kernel launches since the last call; resets the counter */
 long long s3r_engine_take_launches(s3r_engine* e);

@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("ht_w", _vp), ("ht_b", _vp), ("ht_pts", _vp), ("ht_conf", _vp),
         ("ln_stats", _vp), ("ln_np", _i), ("ln_eps", _f), ("ln_cs", _vp), ("a_swap", _i),
         ("stats_out", _vp),
+        ("trace", _vp),
     ]
 
 

@@ -129,24 +129,32 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp runs the uniform control flow, one elected lane issues, and the TMEM / smem bases go
+    // through a shuffle so the compiler can prove them uniform -- otherwise every tcgen05.mma sits in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~80 cycles each, see gemm.cu).
+    {
       constexpr uint32_t idesc_s = umma_idesc(kFmtTF32, BQ, BKV);
       constexpr uint32_t idesc_o = umma_idesc(kFmtTF32, BQ, D);
-      const uint32_t aQ = smem_u32(sQ);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t aQ = __shfl_sync(0xffffffffu, smem_u32(sQ), 0);
+      const uint32_t aKV = __shfl_sync(0xffffffffu, smem_u32(sKV), 0);
       auto issue_s = [&](int j) {   // S_g = Q K_j^T, g = j & 1
         const int st = j % KV_STAGES;
         mbar_wait(&kv_full[st], (j / KV_STAGES) & 1);
         tc_fence_after_sync();
-        const uint32_t aK = smem_u32(sKV + st * (K_BYTES + V_BYTES));
-        const uint32_t tmem_s = tmem_base + (j & 1) * 192;
+        if (elect_one()) {
+          const uint32_t aK = aKV + st * (K_BYTES + V_BYTES);
+          const uint32_t tmem_s = tmem_u + (j & 1) * 192;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const uint64_t dq = umma_desc_sw128_kmajor(aQ + a * (Q_BYTES / 2));
-          const uint64_t dk = umma_desc_sw128_kmajor(aK + a * (K_BYTES / 2));
+          for (int a = 0; a < 2; ++a) {
+            const uint64_t dq = umma_desc_sw128_kmajor(aQ + a * (Q_BYTES / 2));
+            const uint64_t dk = umma_desc_sw128_kmajor(aK + a * (K_BYTES / 2));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, (a | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, (a | kk) != 0);
+          }
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&s_full[j & 1]);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -156,17 +164,20 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
         const int st = j % KV_STAGES;
         mbar_wait(&p_full[g], (j >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t aV = smem_u32(sKV + st * (K_BYTES + V_BYTES) + K_BYTES);
-        const uint32_t tmem_p = tmem_base + g * 192, tmem_o = tmem_p + 128;
+        if (elect_one()) {
+          const uint32_t aV = aKV + st * (K_BYTES + V_BYTES) + K_BYTES;
+          const uint32_t tmem_p = tmem_u + g * 192, tmem_o = tmem_p + 128;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const uint64_t dv = umma_desc_sw128_kmajor(aV + a * (V_BYTES / 4));
+          for (int a = 0; a < 4; ++a) {
+            const uint64_t dv = umma_desc_sw128_kmajor(aV + a * (V_BYTES / 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_tf32_ts(tmem_o, tmem_p + a * 32 + kk * 8, dv + 2 * kk, idesc_o, (j >= 2) || (a | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_tf32_ts(tmem_o, tmem_p + a * 32 + kk * 8, dv + 2 * kk, idesc_o, (j >= 2) || (a | kk) != 0);
+          }
+          umma_commit(&o_full[g]);
+          umma_commit(&kv_empty[st]);
         }
-        umma_commit(&o_full[g]);
-        umma_commit(&kv_empty[st]);
+        __syncwarp();
         if (j + 2 < nblk) issue_s(j + 2);   // same group's next block: its S/P columns are free once PV_j retires
       }
     }
@@ -296,11 +307,7 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
           uint32_t ph[32], pl[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            __nv_bfloat16 ah, al, bh2, bl;
-            split_bf16(o[2 * i], ah, al);
-            split_bf16(o[2 * i + 1], bh2, bl);
-            ph[i] = pack_bf16(ah, bh2);
-            pl[i] = pack_bf16(al, bl);
+            split2_bf16(o[2 * i], o[2 * i + 1], ph[i], pl[i]);
           }
           uint4* hp = reinterpret_cast<uint4*>(args.o_hi + off);
           uint4* lp = reinterpret_cast<uint4*>(args.o_lo + off);

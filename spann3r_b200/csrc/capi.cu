@@ -121,6 +121,7 @@ static int fill_plan(const s3r_gemm_desc* d, GemmPlan* plan) {
     }
     a.stats_out = reinterpret_cast<float2*>(d->stats_out);
   }
+  a.trace = reinterpret_cast<unsigned long long*>(d->trace);
   return 0;
 }
 

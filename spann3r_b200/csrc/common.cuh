@@ -39,6 +39,17 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// two values at once on the packed converter (F2FP.BF16.PACK_AB, full ALU rate; the scalar F2F.BF16.F32 the single-
+// value form compiles to runs on the quarter-rate conversion pipe): hi / lo = packed bf16x2, first value in the low half.
+// Bit-identical to split_bf16 on each value.
+__device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+  const float ah = __uint_as_float(hu << 16), bh = __uint_as_float(hu & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+  hi = hu;
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -48,10 +59,15 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// not inlined on purpose: the unrolled epilogues call it 32x per chunk and erff is ~100 instructions; keeping the GEMM
-// kernels small (instruction cache) matters more than the call overhead in the epilogue warps
-static __device__ __noinline__ float gelu_erf(float x) {
+// exact-erf GELU (nn.GELU default, croco/models/blocks.py:73-79).  Four values per call, not inlined: one call per
+// element serialises ~35 dependent instructions 32 times per chunk (no ILP across calls: measured ~12 us of the
+// decoder's fc1 launches), full inlining of 32 copies bloats every epilogue instantiation; four independent chains per
+// call hide the FFMA latency at a quarter of the calls.
+__device__ __forceinline__ float gelu_erf1(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+static __device__ __noinline__ float4 gelu_erf4(float4 x) {
+  return make_float4(gelu_erf1(x.x), gelu_erf1(x.y), gelu_erf1(x.z), gelu_erf1(x.w));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -130,6 +146,26 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
       "[%2];" ::"r"(smem_u32(smem)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Variants on raw shared-memory addresses (warp-uniform producers keep them in uniform registers)
+__device__ __forceinline__ void mbar_arrive_expect_tx_u(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_u(uint32_t smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_u(uint32_t smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -226,6 +262,12 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // 128-bit global stores / loads
 __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float d) {

@@ -380,6 +380,27 @@ double s3r_engine_take_flops(s3r_engine* e) {
 }
 void s3r_engine_profile(s3r_engine* e, int on) { e->profiling = on != 0; }
 
+// Synchronises and copies out the per-launch CUDA-event durations recorded while profiling was on (without
+// consuming them: follow with s3r_engine_profile_read).  Returns the number of launches recorded (may exceed cap).
+int s3r_engine_profile_list(s3r_engine* e, double* ms, double* flops, int* kind, int cap) {
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("profile_list: %s", cudaGetErrorString(cudaGetLastError()));
+    return -6;
+  }
+  int n = 0;
+  for (auto& t : e->timed) {
+    if (n < cap) {
+      float v = 0.f;
+      cudaEventElapsedTime(&v, t.a, t.b);
+      ms[n] = v;
+      flops[n] = t.flops;
+      kind[n] = t.kind;
+    }
+    ++n;
+  }
+  return n;
+}
+
 // Synchronises, then sums CUDA-event durations of the launches recorded while profiling was on.
 // out[0..3] = {gemm_ms, gemm_flops, gemm_launches, attn_ms}, out[4..5] = {attn_flops, attn_launches}
 int s3r_engine_profile_read(s3r_engine* e, double* out) {

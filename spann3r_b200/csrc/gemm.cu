@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* const trace = (blockIdx.x == 0) ? args.trace : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
   const int n_tiles = (args.N + BN - 1) / BN;
   const int m_tiles = args.tiles_w * args.tiles_h * args.NB;
@@ -90,11 +92,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
+  if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // whole warp in uniform control flow, one elected lane issues (same reason as the MMA warp below: no
+    // per-instruction ELECT / R2UR waterfall); tap / channel coordinates advance incrementally, no div / mod per k-block
+    {
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t full_u = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -108,21 +116,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         const int w0 = tw * args.bw, h0 = th * args.bh;
         const int img = (args.a_swap ? (args.groups - 1 - g) : g) * args.NB + nb;
         const int brow = g * args.b_group_rows + nt * BN;
+        int tap = 0, kc = 0, dx = (args.taps == 9) ? -1 : 0, dy = dx;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / args.kpt;
-          const int kc = (kb - tap * args.kpt) * BK;
-          int dx = 0, dy = 0;
-          if (args.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* s = smem + stage * Cfg::STAGE;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
-          tma_load_4d(s, &args.tmA_hi, &full_bar[stage], kc, w0 + dx, h0 + dy, img);
-          tma_load_4d(s + Cfg::A_TILE, &args.tmA_lo, &full_bar[stage], kc, w0 + dx, h0 + dy, img);
-          tma_load_3d(s + 2 * Cfg::A_TILE, &args.tmB_hi, &full_bar[stage], kc, tap, brow);
-          tma_load_3d(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, &full_bar[stage], kc, tap, brow);
+          if (elect_one()) {
+            const uint32_t s = smem_u + stage * Cfg::STAGE;
+            const uint32_t fb = full_u + stage * 8;
+            mbar_arrive_expect_tx_u(fb, Cfg::STAGE);
+            tma_load_4d_u(s, &args.tmA_hi, fb, kc, w0 + dx, h0 + dy, img);
+            tma_load_4d_u(s + Cfg::A_TILE, &args.tmA_lo, fb, kc, w0 + dx, h0 + dy, img);
+            tma_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
+            tma_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+          }
+          __syncwarp();
+          kc += BK;
+          if (kc >= args.kpt * BK) {   // next tap: (dy, dx) walk the 3x3 window row by row
+            kc = 0;
+            ++tap;
+            if (++dx > 1) {
+              dx = -1;
+              ++dy;
+            }
+          }
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -132,8 +147,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp runs the (warp-uniform) control flow and one elected lane issues; the TMEM / smem base
+    // addresses go through a shuffle so that the compiler can prove them uniform.  With a plain `if (lane == 0)` and a
+    // TMEM address loaded from shared memory ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+    // waterfall loop that costs ~80 cycles per MMA -- more than a 128 x 64 or 128 x 128 MMA takes to execute
+    // (tools/fill_probe.py: 517 ns per k-block whatever the tile width); now the 12 MMAs of a k-block are
+    // back-to-back UTCHMMA instructions.
+    {
       constexpr uint32_t idesc = umma_idesc(kFmtBF16, BM, BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -142,29 +165,35 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_u + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
-          const uint64_t da_hi = umma_desc_sw128_kmajor(sa);
-          const uint64_t da_lo = umma_desc_sw128_kmajor(sa + Cfg::A_TILE);
-          const uint64_t db_hi = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE);
-          const uint64_t db_lo = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE + Cfg::B_TILE);
+          if (trace && kb == 0 && it == 0 && lane == 0) trace[3] = globaltimer_ns();
+          if (elect_one()) {
+            const uint32_t sa = smem_u + stage * Cfg::STAGE;
+            const uint64_t da_hi = umma_desc_sw128_kmajor(sa);
+            const uint64_t da_lo = umma_desc_sw128_kmajor(sa + Cfg::A_TILE);
+            const uint64_t db_hi = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE);
+            const uint64_t db_lo = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE + Cfg::B_TILE);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t ko = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle span
-            umma_bf16(tmem_d, da_hi + ko, db_lo + ko, idesc, (kb | kk) != 0);
-            umma_bf16(tmem_d, da_lo + ko, db_hi + ko, idesc, 1);
-            umma_bf16(tmem_d, da_hi + ko, db_hi + ko, idesc, 1);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t ko = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle span
+              umma_bf16(tmem_d, da_hi + ko, db_lo + ko, idesc, (kb | kk) != 0);
+              umma_bf16(tmem_d, da_lo + ko, db_hi + ko, idesc, 1);
+              umma_bf16(tmem_d, da_hi + ko, db_hi + ko, idesc, 1);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);
+        if (elect_one()) umma_commit(&tmem_full[as]);
+        __syncwarp();
+        if (trace && it == 0 && lane == 0) trace[7] = globaltimer_ns();
       }
     }
   } else {
@@ -210,6 +239,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
+      if (trace && it == 0 && threadIdx.x == 64) trace[4] = globaltimer_ns();
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
 
       float ht_acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -221,14 +251,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         tmem_ld_32x32(tbase + c * 32, raw);
         if (c + 1 < BN / 32 && col0 + 32 < args.N) epi_prefetch_res<EPI>(args, rnxt, grow, valid, col0 + 32);
         tmem_ld_wait();
+        if (trace && it == 0 && c == 0 && threadIdx.x == 64) trace[8] = globaltimer_ns();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
         epi_chunk<EPI>(args, v, sb + c * 32, scs + c * 32, er, rcur, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+        if (trace && it == 0 && c == 0 && threadIdx.x == 64) trace[9] = globaltimer_ns();
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
       }
+      if (trace && it == 0 && threadIdx.x == 64) trace[10] = globaltimer_ns();
       // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
@@ -248,12 +281,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
     }
   }
 
+  if (trace && threadIdx.x == 64) trace[5] = globaltimer_ns();   // epilogue of this CTA's last tile done
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+  if (trace && threadIdx.x == 0) trace[6] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -47,6 +47,8 @@ struct GemmArgs {
   int a_swap;                         // 1: group g reads the A rows (and statistics) of group G-1-g (norm_y of the twin decoders)
   // Producer side (EPI_PLAIN): write (sum, sum of squares) of every output row chunk, [rows, N/32]
   float2* stats_out;
+  // optional timeline of CTA 0 (tools/trace_gemm.py): 8 x %globaltimer stamps, null = off
+  unsigned long long* trace;
   // EPI_PIXSHUF
   int ps_s, ps_cout;
   // EPI_QKV

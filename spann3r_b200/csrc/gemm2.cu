@@ -58,6 +58,22 @@ __device__ __forceinline__ void tma2_load_3d(void* smem, const CUtensorMap* m, u
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// raw shared-address variants for the warp-uniform producer (bar: this CTA's address of the barrier)
+__device__ __forceinline__ void tma2_load_4d_u(uint32_t smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                               int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d_u(uint32_t smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // arrive on the same-offset mbarrier of CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
@@ -149,7 +165,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // whole warp in uniform control flow, one elected lane issues; incremental tap / channel coordinates (see gemm.cu)
+    {
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t full_u = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
@@ -164,22 +183,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         const int w0 = tw * args.bw, h0 = th * args.bh;
         const int img = (args.a_swap ? (args.groups - 1 - g) : g) * args.NB + nb;
         const int brow = g * args.b_group_rows + nt * BN + (int)rank * (BN / 2);
+        int tap = 0, kc = 0, dx = (args.taps == 9) ? -1 : 0, dy = dx;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / args.kpt;
-          const int kc = (kb - tap * args.kpt) * BK;
-          int dx = 0, dy = 0;
-          if (args.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
-          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* s = smem + stage * Cfg::STAGE;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE);
-          else mbar_arrive_remote(&full_bar[stage], 0);
-          tma2_load_4d(s, &args.tmA_hi, &full_bar[stage], kc, w0 + dx, h0 + dy, img);
-          tma2_load_4d(s + Cfg::A_TILE, &args.tmA_lo, &full_bar[stage], kc, w0 + dx, h0 + dy, img);
-          tma2_load_3d(s + 2 * Cfg::A_TILE, &args.tmB_hi, &full_bar[stage], kc, tap, brow);
-          tma2_load_3d(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, &full_bar[stage], kc, tap, brow);
+          if (elect_one()) {
+            const uint32_t s = smem_u + stage * Cfg::STAGE;
+            const uint32_t fb = full_u + stage * 8;
+            if (leader) mbar_arrive_expect_tx_u(fb, 2 * Cfg::STAGE);
+            else mbar_arrive_remote(&full_bar[stage], 0);
+            tma2_load_4d_u(s, &args.tmA_hi, fb, kc, w0 + dx, h0 + dy, img);
+            tma2_load_4d_u(s + Cfg::A_TILE, &args.tmA_lo, fb, kc, w0 + dx, h0 + dy, img);
+            tma2_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
+            tma2_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+          }
+          __syncwarp();
+          kc += BK;
+          if (kc >= args.kpt * BK) {
+            kc = 0;
+            ++tap;
+            if (++dx > 1) {
+              dx = -1;
+              ++dy;
+            }
+          }
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -188,9 +214,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // whole warp in uniform control flow, one elected lane issues, bases made provably uniform (see gemm.cu)
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc(kFmtBF16, 2 * BM, BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -199,29 +228,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_u + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
-          const uint64_t da_hi = umma_desc_sw128_kmajor(sa);
-          const uint64_t da_lo = umma_desc_sw128_kmajor(sa + Cfg::A_TILE);
-          const uint64_t db_hi = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE);
-          const uint64_t db_lo = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE + Cfg::B_TILE);
+          if (elect_one()) {
+            const uint32_t sa = smem_u + stage * Cfg::STAGE;
+            const uint64_t da_hi = umma_desc_sw128_kmajor(sa);
+            const uint64_t da_lo = umma_desc_sw128_kmajor(sa + Cfg::A_TILE);
+            const uint64_t db_hi = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE);
+            const uint64_t db_lo = umma_desc_sw128_kmajor(sa + 2 * Cfg::A_TILE + Cfg::B_TILE);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t ko = (uint64_t)(kk * 32 >> 4);
-            umma2_bf16(tmem_d, da_hi + ko, db_lo + ko, idesc, (kb | kk) != 0);
-            umma2_bf16(tmem_d, da_lo + ko, db_hi + ko, idesc, 1);
-            umma2_bf16(tmem_d, da_hi + ko, db_hi + ko, idesc, 1);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t ko = (uint64_t)(kk * 32 >> 4);
+              umma2_bf16(tmem_d, da_hi + ko, db_lo + ko, idesc, (kb | kk) != 0);
+              umma2_bf16(tmem_d, da_lo + ko, db_hi + ko, idesc, 1);
+              umma2_bf16(tmem_d, da_hi + ko, db_hi + ko, idesc, 1);
+            }
+            umma2_commit_mc(&empty_bar[stage]);   // frees this smem slot in BOTH CTAs
           }
-          umma2_commit_mc(&empty_bar[stage]);   // frees this smem slot in BOTH CTAs
+          __syncwarp();
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma2_commit_mc(&tmem_full[as]);        // accumulator ready in BOTH CTAs
+        if (elect_one()) umma2_commit_mc(&tmem_full[as]);        // accumulator ready in BOTH CTAs
+        __syncwarp();
       }
     }
   } else {

@@ -6,10 +6,20 @@
 
 namespace s3r {
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_GELU) return gelu_erf(v);
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  return v;
+__device__ __forceinline__ void apply_act(float (&v)[32], int act) {
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = gelu_erf4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      v[4 * q] = t.x;
+      v[4 * q + 1] = t.y;
+      v[4 * q + 2] = t.z;
+      v[4 * q + 3] = t.w;
+    }
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
 }
 
 // Per-tile column vectors staged in shared memory by the epilogue warps BEFORE they wait for the accumulator (the
@@ -44,12 +54,18 @@ __device__ __forceinline__ void epi_row_init(const GemmArgs& args, EpiRow& er, i
                                              bool valid) {
   if (args.ln_stats != nullptr && valid) {
     const int ga = args.a_swap ? (args.groups - 1 - g) : g;
-    const float2* sp = args.ln_stats + ((long long)ga * args.out_group_rows + pix) * args.ln_np;
+    // ln_np <= 32 chunk pairs (C <= 1024, even count): all loads are issued before the first add (a rolled loop
+    // would serialise ln_np dependent L2 round trips); fixed summation order
+    const float4* sp = reinterpret_cast<const float4*>(args.ln_stats + ((long long)ga * args.out_group_rows + pix) * args.ln_np);
+    const int np2 = args.ln_np >> 1;
+    float4 t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = (i < np2) ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < args.ln_np; ++i) {
-      const float2 t = sp[i];
-      s1 += t.x;
-      s2 += t.y;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s1 += t[i].x + t[i].z;
+      s2 += t[i].y + t[i].w;
     }
     const float inv_c = 1.0f / (float)(args.ln_np * 32);
     const float mean = s1 * inv_c;
@@ -86,15 +102,28 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
                                           const EpiRow& er, const float4 (&rp)[8], int g, int nb, int h, int w,
                                           bool valid, long long pix, long long grow, int col0, float (&ht_acc)[4]) {
   if (args.ln_stats != nullptr) {
+    const float4* c4 = reinterpret_cast<const float4*>(scs);   // 128-byte aligned chunk of the staged columns
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaf(er.rstd, v[j], -er.rm * scs[j]);
+    for (int q = 0; q < 8; ++q) {
+      const float4 c = c4[q];
+      v[4 * q + 0] = fmaf(er.rstd, v[4 * q + 0], -er.rm * c.x);
+      v[4 * q + 1] = fmaf(er.rstd, v[4 * q + 1], -er.rm * c.y);
+      v[4 * q + 2] = fmaf(er.rstd, v[4 * q + 2], -er.rm * c.z);
+      v[4 * q + 3] = fmaf(er.rstd, v[4 * q + 3], -er.rm * c.w);
+    }
   }
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] += sb[j];
-  if (args.act != ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], args.act);
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = b4[q];
+      v[4 * q + 0] += b.x;
+      v[4 * q + 1] += b.y;
+      v[4 * q + 2] += b.z;
+      v[4 * q + 3] += b.w;
+    }
   }
+  if (args.act != ACT_NONE) apply_act(v, args.act);
 
   if constexpr (EPI == EPI_PLAIN || EPI == EPI_PIXSHUF) {
     long long orow = grow;
@@ -165,11 +194,7 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
             a = fmaxf(a, 0.f);
             b = fmaxf(b, 0.f);
           }
-          __nv_bfloat16 ah, al, bh, bl;
-          split_bf16(a, ah, al);
-          split_bf16(b, bh, bl);
-          ph[q] = pack_bf16(ah, bh);
-          pl[q] = pack_bf16(al, bl);
+          split2_bf16(a, b, ph[q], pl[q]);
         }
         const long long po = orow * args.ldp + args.plane_col0 + ocol;
         uint4* hp = reinterpret_cast<uint4*>(args.out_hi + po);

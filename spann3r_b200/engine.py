@@ -83,6 +83,7 @@ _lib.register_protos({
     "s3r_engine_take_launches": (C.c_longlong, [_vp]),
     "s3r_engine_profile": (None, [_vp, _i]),
     "s3r_engine_profile_read": (_i, [_vp, C.POINTER(C.c_double)]),
+    "s3r_engine_profile_list": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i), _i]),
 })
 
 ROPE_MAXPOS = 64
@@ -388,6 +389,14 @@ class Engine:
         _lib.check(_lib.lib().s3r_engine_profile_read(self._h, out), "profile_read")
         return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), attn_ms=out[3], attn_flops=out[4],
                     attn_launches=int(out[5]))
+
+    def profile_list(self, cap: int = 4096):
+        """[(ms, flops, kind)] of the launches recorded since profile(True), in launch order (kind 0 GEMM, 1 attention)."""
+        ms, fl, kd = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_int * cap)()
+        n = _lib.lib().s3r_engine_profile_list(self._h, ms, fl, kd, cap)
+        if n < 0:
+            _lib.check(n, "profile_list")
+        return [(ms[i], fl[i], kd[i]) for i in range(min(n, cap))]
 
     def take_launches(self) -> int:
         return int(_lib.lib().s3r_engine_take_launches(self._h))
