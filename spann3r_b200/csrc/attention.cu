@@ -66,7 +66,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
   using namespace attn;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would lose the address
+  // space and turn every access through `smem` into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;                            // stage s: K at s*(K+V), V after K
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KV_STAGES * (K_BYTES + V_BYTES));
@@ -295,26 +297,33 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
       const float inv = 1.0f / (l * w0 + l1 * w1);
 #pragma unroll
       for (int i = 0; i < D; ++i) o[i] = (o[i] * w0 + mg[i * 128 + r] * w1) * inv;
-      const int q = q0 + r;
-      if (q < args.nq) {
-        const int b = bh / args.heads, h = bh - b * args.heads;
-        const long long off = ((long long)b * args.nq + q) * args.ldo + h * D;
-        if (args.o_f32) {
+      // Transposed store (see gemm_epilogue.cuh): thread = row would touch 32 different cache lines per 16-byte
+      // access; stage the warp's 32 x 64 tile in the drained KV ring (behind the merge buffer) and write it so that
+      // 16 consecutive lanes cover one row's 256 bytes.
+      constexpr int LD = D + 4;
+      float* stg = reinterpret_cast<float*>(sKV + 40 * 1024) + quad * 32 * LD;
+      {
+        float4* sp = reinterpret_cast<float4*>(stg + lane * LD);
 #pragma unroll
-          for (int i = 0; i < D; i += 4) st_f4(args.o_f32 + off + i, o[i], o[i + 1], o[i + 2], o[i + 3]);
-        }
-        if (args.o_hi) {
-          uint32_t ph[32], pl[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            split2_bf16(o[2 * i], o[2 * i + 1], ph[i], pl[i]);
-          }
-          uint4* hp = reinterpret_cast<uint4*>(args.o_hi + off);
-          uint4* lp = reinterpret_cast<uint4*>(args.o_lo + off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            hp[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-            lp[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+        for (int i = 0; i < D / 4; ++i) sp[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      __syncwarp();
+      const int b = bh / args.heads, h = bh - b * args.heads;
+      const int cq = (lane & 15) * 4;
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const int rr = it * 2 + (lane >> 4);
+        const int q = q0 + quad * 32 + rr;
+        if (q < args.nq) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + rr * LD + cq);
+          const long long off = ((long long)b * args.nq + q) * args.ldo + h * D + cq;
+          if (args.o_f32) *reinterpret_cast<float4*>(args.o_f32 + off) = x;
+          if (args.o_hi) {
+            uint32_t h0, l0, h1, l1;
+            split2_bf16(x.x, x.y, h0, l0);
+            split2_bf16(x.z, x.w, h1, l1);
+            *reinterpret_cast<uint2*>(args.o_hi + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(args.o_lo + off) = make_uint2(l0, l1);
           }
         }
       }

@@ -74,7 +74,7 @@ static int fill_plan(const s3r_gemm_desc* d, GemmPlan* plan) {
     set_error("s3r_gemm: EPI_HEADTAIL needs n == 128");
     return -1;
   }
-  const int force_bn = d->epi == S3R_EPI_HEADTAIL ? 128 : d->force_bn;
+  const int force_bn = d->epi == S3R_EPI_HEADTAIL ? (d->force_bn == 128 ? 128 : 1128) : d->force_bn;
   int r = gemm_plan_init(plan, B(d->a_hi), B(d->a_lo), B(d->b_hi), B(d->b_lo), d->groups, d->nb, d->h, d->w, d->kc,
                          d->taps, d->n, force_bn);
   if (r) return r;

@@ -143,7 +143,7 @@ struct s3r_engine {
     if (pc.building) {
       pc.gemms.emplace_back();
       int r = gemm_plan_init(&pc.gemms.back(), A.hi, A.lo, Bw.hi, Bw.lo, g.groups, g.NB, g.H, g.W, g.Kc, g.taps, g.N,
-                             e.epi == EPI_HEADTAIL ? 128 : g.force_bn, g.lda, g.ldb, g.b_group_rows);
+                             e.epi == EPI_HEADTAIL ? 1128 : g.force_bn, g.lda, g.ldb, g.b_group_rows);
       if (r) return r;
     }
     if (pc.gc >= pc.gemms.size()) {

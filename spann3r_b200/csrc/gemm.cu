@@ -32,7 +32,9 @@ namespace s3r {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kNumThreads = 192;
+static constexpr int kEpiWarps = 8;     // 2 per SM sub-partition: the epilogue is a chain of dependent instructions, a second
+                                        // warp per scheduler hides its latencies (tools/trace_gemm.py)
+static constexpr int kNumThreads = 64 + 32 * kEpiWarps;
 static constexpr int kSmemRing = 192 * 1024;
 
 template <int BN>
@@ -42,7 +44,9 @@ struct GemmCfg {
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = kSmemRing / STAGE;
   static constexpr int COLV = 2 * 2 * BN * 4;  // per accumulator stage: staged bias + LN-fold column sums of the tile
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + COLV;
+  static constexpr int SW = 16;                // epilogue staging width (gemm_epilogue.cuh)
+  static constexpr int STG = kEpiWarps * Stg<SW>::WARP_BYTES;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + COLV + STG;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
 };
 
@@ -51,7 +55,9 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would lose the address
+  // space and turn every access through `smem` into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -197,18 +203,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9): TMEM lane quadrant
+    // warp & 3, column half (warp - 2) >> 2
     if (args.pf_bytes) {   // pull the next GEMM's weights into L2 while this kernel's main loop runs
       const unsigned long long lines = args.pf_bytes >> 7;
-      for (unsigned long long ln = (unsigned long long)blockIdx.x * 128 + (threadIdx.x - 64); ln < lines;
-           ln += (unsigned long long)gridDim.x * 128) {
+      for (unsigned long long ln = (unsigned long long)blockIdx.x * (32 * kEpiWarps) + (threadIdx.x - 64); ln < lines;
+           ln += (unsigned long long)gridDim.x * (32 * kEpiWarps)) {
         prefetch_l2(args.pf_base0 + (ln << 7));
         prefetch_l2(args.pf_base1 + (ln << 7));
       }
     }
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int r = quad * 32 + lane;
-    const int dh = r / args.bw, dw = r - dh * args.bw;
+    const int half = (warp - 2) >> 2;
+    constexpr int CH = BN / 64;  // 32-column chunks per warp
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -220,22 +227,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
       const int tw = mt % args.tiles_w;
       const int th = (mt / args.tiles_w) % args.tiles_h;
       const int nb = mt / (args.tiles_w * args.tiles_h);
-      const int h = th * args.bh + dh, w = tw * args.bw + dw;
-      const bool valid = (h < args.H) && (w < args.W);
-      const long long pix = ((long long)nb * args.H + h) * args.W + w;  // row inside the group
-      const long long grow = (long long)g * args.out_group_rows + pix;  // global output row (PLAIN)
 
       // everything that does not need the accumulator is requested while the main loop of this tile still runs:
-      // the tile's bias / colsum columns (-> smem), the row's LayerNorm statistics and RoPE position, and the
-      // residual values of the first chunk
+      // the tile's bias / colsum columns (-> smem), the rows' LayerNorm statistics, RoPE positions and output
+      // addresses, and the residual values of the first chunk
+      constexpr int SW = Cfg::SW;
       float* sb = colv + as * 2 * BN;
       float* scs = sb + BN;
-      epi_stage_cols<EPI, BN>(args, sb, scs, g, nt, (int)threadIdx.x - 64, 128);
+      float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(colv) + Cfg::COLV + (warp - 2) * Stg<SW>::WARP_BYTES);
+      epi_stage_cols<EPI, BN>(args, sb, scs, g, nt, (int)threadIdx.x - 64, 32 * kEpiWarps);
+      const TileGeom tg = make_geom(args, g, nb, th, tw);
       EpiRow er;
-      epi_row_init<EPI>(args, er, g, pix, grow, valid);
+      EpiTRows tr;
+      epi_tile_pre<EPI, SW>(args, tg, quad, lane, er, tr);
       float4 rcur[8], rnxt[8];
-      if (nt * BN < args.N) epi_prefetch_res<EPI>(args, rcur, grow, valid, nt * BN);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // staged columns visible to the 4 epilogue warps
+      const int cfirst = nt * BN + half * CH * 32;
+      if (cfirst < args.N) epi_prefetch_res<EPI, SW>(args, tr, rcur, cfirst, lane);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // staged columns visible to all epilogue warps
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
@@ -244,20 +252,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
 
       float ht_acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < CH; ++cc) {
+        const int c = half * CH + cc;
         const int col0 = nt * BN + c * 32;
         if (col0 >= args.N) break;  // warp-uniform
         uint32_t raw[32];
         tmem_ld_32x32(tbase + c * 32, raw);
-        if (c + 1 < BN / 32 && col0 + 32 < args.N) epi_prefetch_res<EPI>(args, rnxt, grow, valid, col0 + 32);
+        if (cc + 1 < CH && col0 + 32 < args.N) epi_prefetch_res<EPI, SW>(args, tr, rnxt, col0 + 32, lane);
         tmem_ld_wait();
-        if (trace && it == 0 && c == 0 && threadIdx.x == 64) trace[8] = globaltimer_ns();
+        if (trace && it == 0 && cc == 0 && threadIdx.x == 64) trace[8] = globaltimer_ns();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 
-        epi_chunk<EPI>(args, v, sb + c * 32, scs + c * 32, er, rcur, g, nb, h, w, valid, pix, grow, col0, ht_acc);
-        if (trace && it == 0 && c == 0 && threadIdx.x == 64) trace[9] = globaltimer_ns();
+        epi_chunk<EPI, SW>(args, v, sb + c * 32, scs + c * 32, stg, tg, er, tr, rcur, col0, lane, ht_acc);
+        if (trace && it == 0 && cc == 0 && threadIdx.x == 64) trace[9] = globaltimer_ns();
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
       }
@@ -267,16 +276,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
 
-      if (EPI == EPI_HEADTAIL && valid) {
-        const float* b4 = args.ht_b + g * 4;
-        const float x = ht_acc[0] + b4[0], y = ht_acc[1] + b4[1], z = ht_acc[2] + b4[2], cf = ht_acc[3] + b4[3];
-        const float d = sqrtf(x * x + y * y + z * z);
-        const float sc = expm1f(d) / fmaxf(d, 1e-8f);
-        float* pp = args.ht_pts + grow * 3;
-        pp[0] = x * sc;
-        pp[1] = y * sc;
-        pp[2] = z * sc;
-        args.ht_conf[grow] = 1.0f + expf(cf);
+      if constexpr (EPI == EPI_HEADTAIL) {
+        // the row's 4 dot products are split over the two column halves: half 1 hands its partial sums to half 0
+        // through its staging tile (two alternating slots), 64-thread named barrier per lane quadrant
+        uint8_t* stg_base = reinterpret_cast<uint8_t*>(colv) + Cfg::COLV;
+        float4* slot = reinterpret_cast<float4*>(stg_base + (4 + quad) * Stg<SW>::WARP_BYTES) + (it & 1) * 32;
+        if (half == 1) slot[lane] = make_float4(ht_acc[0], ht_acc[1], ht_acc[2], ht_acc[3]);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        if (half == 0) {
+          const float4 p = slot[lane];
+          ht_acc[0] += p.x; ht_acc[1] += p.y; ht_acc[2] += p.z; ht_acc[3] += p.w;
+          epi_headtail_finish(args, tg, er, ht_acc);
+        }
       }
     }
   }
@@ -385,28 +396,31 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   a.tiles_w = (W + a.bw - 1) / a.bw;
   a.tiles_h = (H + a.bh - 1) / a.bh;
   a.out_group_rows = (long long)NB * H * W;
-  // Tile shape.  Measured on B200 (tools/gemm_sweep.py): the engine is bound by operand bytes
-  // through L2 -> SMEM, so prefer the 2-CTA kernel (256 x bn pair tiles: each SM stages only half of B) whenever the
-  // m-tile count is even; otherwise 1-CTA tiles as wide as still leaves ~3/4 of the SMs busy.
+  // Tile shape: the cheapest of {128 x 64, 128 x 128 (1 CTA), 256 x 128 (CTA pair)} under a two-constant model fitted to
+  // tools/gemm_sweep.py / conv_sweep.py on B200 (profiles/r1_tile_sweep.md): makespan = waves x k-blocks x period, with
+  // waves = ceil(tiles / CTAs (148) or CTA pairs (74)) for the persistent static schedule and the measured k-block
+  // periods 0.45 us (128 x 64), 0.62 us (128 x 128), 0.58 us (256 x 128 per pair: each SM stages only half of B).
+  // 256-wide tiles never win any more (two-stage ring), so they are only reachable through force_bn.
   const long long m_tiles = (long long)a.tiles_w * a.tiles_h * NB * groups;
   const long long m_tiles_group = (long long)a.tiles_w * a.tiles_h * NB;
-  int bn = 128, two = 0;
-  if (N >= 256 && m_tiles * ((N + 255) / 256) >= 2 * num_sms()) bn = 256;
-  else if (m_tiles * ((N + 127) / 128) < (3 * num_sms()) / 4 && N >= 64) bn = 64;
-  if (N <= 64) bn = 64;
-  static const int g2_mode = getenv("S3R_GEMM2") ? atoi(getenv("S3R_GEMM2")) : 1;   // 0 off, 1 auto, 128/256 fixed
-  // 2-CTA pair tiles pay off once there are several waves of tiles (measured: +8..12% on the M=7680 encoder GEMMs,
-  // nothing at M=768 where fixed per-kernel costs dominate); g2_mode 128/256 forces them wherever they are legal.
-  const long long tiles128 = m_tiles * ((N + 127) / 128);
+  const int sms = num_sms();
+  auto waves = [](long long tiles, long long slots) { return (double)((tiles + slots - 1) / slots); };
+  const long long nt64 = (N + 63) / 64, nt128 = (N + 127) / 128;
+  const double c64 = waves(m_tiles * nt64, sms) * 0.45;
+  const double c128 = (N > 64) ? waves(m_tiles * nt128, sms) * 0.62 : 1e30;
   const bool legal2 = (m_tiles_group % 2 == 0) && N >= 128;
-  static const int g2_conv = getenv("S3R_GEMM2_CONV") ? atoi(getenv("S3R_GEMM2_CONV")) : 0;   // 1: also 3x3 convs
-  if (force_bn == 0 && legal2 &&
-      ((g2_mode == 1 && (taps == 1 || g2_conv) && tiles128 >= 400) || g2_mode == 128 || g2_mode == 256)) {
+  static const int g2_mode = getenv("S3R_GEMM2") ? atoi(getenv("S3R_GEMM2")) : 1;   // 0 off, 1 auto, 128/256 fixed
+  const double c2128 = (legal2 && g2_mode != 0) ? waves(m_tiles / 2 * nt128, sms / 2) * 0.58 : 1e30;
+  int bn = 64, two = 0;
+  if (c128 < c64) bn = 128;
+  if (c2128 <= (bn == 64 ? c64 : c128)) { bn = 128; two = 1; }
+  if (N <= 64) { bn = 64; two = 0; }
+  if (force_bn == 0 && legal2 && (g2_mode == 128 || g2_mode == 256)) {
     two = 1;
-    bn = (N >= 256 && N % 256 == 0) ? 256 : 128;
-    if (g2_mode == 128) bn = 128;
+    bn = (g2_mode == 256 && N % 256 == 0) ? 256 : 128;
   }
-  if (force_bn >= 2000) { two = 1; bn = force_bn - 2000; }
+  if (force_bn == 1128) { two = legal2 ? 1 : 0; bn = 128; }   // width 128 (EPI_HEADTAIL), CTA pairs where legal
+  else if (force_bn >= 2000) { two = 1; bn = force_bn - 2000; }
   else if (force_bn > 0) { two = 0; bn = force_bn; }
   if (two && (m_tiles_group % 2 != 0 || (bn != 128 && bn != 256))) {
     set_error("gemm_plan_init: 2-CTA tiles need an even m-tile count per group and bn in {128,256}");

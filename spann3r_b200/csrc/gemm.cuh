@@ -79,7 +79,8 @@ struct GemmPlan {
 // Encodes the four tensor maps and picks the tile shape.  Returns 0 or a negative error.
 // lda / ldb: row strides (elements) of A pixels / B rows (0 = dense: Kc resp. taps*Kc);
 // b_group_rows: rows between consecutive groups of B (0 = N).
-// force_bn: 0 = planner's choice; 64/128/256 = 1-CTA kernel with that tile width; 2128/2256 = 2-CTA kernel (256 x 128/256).
+// force_bn: 0 = planner's choice; 64/128/256 = 1-CTA kernel with that tile width; 2128/2256 = 2-CTA kernel (256 x 128/256);
+// 1128 = width 128 on CTA pairs where legal, else 1 CTA.
 int gemm_plan_init(GemmPlan* plan,
                    const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,   // [G*NB, H, W, Kc]
                    const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo,   // [G*N, taps, Kc]

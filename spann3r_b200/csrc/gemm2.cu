@@ -29,7 +29,9 @@ struct Gemm2Cfg {
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = g2::kSmemRing / STAGE;
   static constexpr int COLV = 2 * 2 * BN * 4;   // per accumulator stage: staged bias + LN-fold column sums of the tile
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + COLV;
+  static constexpr int SW = 16;                 // epilogue staging width: 8 warps x 32 x 32 floats would not fit
+  static constexpr int STG = g2::kEpiWarps * Stg<SW>::WARP_BYTES;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + COLV + STG;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -117,7 +119,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
   using Cfg = Gemm2Cfg<BN>;
   using namespace g2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would lose the address
+  // space and turn every access through `smem` into a generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
   uint64_t* full_bar = bars;                       // used in the leader only (count 2: both producers)
   uint64_t* empty_bar = bars + Cfg::STAGES;        // per CTA, multicast commit from the leader
@@ -269,8 +273,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
     }
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;            // column half handled by this warp
-    const int r = quad * 32 + lane;
-    const int dh = r / args.bw, dw = r - dh * args.bw;
     int it = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++it) {
       const int as = it & 1;
@@ -283,22 +285,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
       const int tw = mt % args.tiles_w;
       const int th = (mt / args.tiles_w) % args.tiles_h;
       const int nb = mt / (args.tiles_w * args.tiles_h);
-      const int h = th * args.bh + dh, w = tw * args.bw + dw;
-      const bool valid = (h < args.H) && (w < args.W);
-      const long long pix = ((long long)nb * args.H + h) * args.W + w;
-      const long long grow = (long long)g * args.out_group_rows + pix;
 
-      // requested while the main loop of this tile still runs (see gemm.cu): staged bias / colsum columns, the
-      // row's LayerNorm statistics and RoPE position, the first chunk's residual values
+      // requested while the main loop of this tile still runs (see gemm.cu): staged bias / colsum columns, the rows'
+      // LayerNorm statistics, RoPE positions and output addresses, the first chunk's residual values
       constexpr int CH = BN / 64;  // 32-column chunks per warp
+      constexpr int SW = Cfg::SW;
       float* sb = colv + as * 2 * BN;
       float* scs = sb + BN;
+      float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(colv) + Cfg::COLV + (warp - 2) * Stg<SW>::WARP_BYTES);
       epi_stage_cols<EPI, BN>(args, sb, scs, g, nt, (int)threadIdx.x - 64, 32 * kEpiWarps);
+      const TileGeom tg = make_geom(args, g, nb, th, tw);
       EpiRow er;
-      epi_row_init<EPI>(args, er, g, pix, grow, valid);
+      EpiTRows tr;
+      epi_tile_pre<EPI, SW>(args, tg, quad, lane, er, tr);
       float4 rcur[8], rnxt[8];
       const int cfirst = nt * BN + half * CH * 32;
-      if (cfirst < args.N) epi_prefetch_res<EPI>(args, rcur, grow, valid, cfirst);
+      if (cfirst < args.N) epi_prefetch_res<EPI, SW>(args, tr, rcur, cfirst, lane);
       asm volatile("bar.sync 1, 256;" ::: "memory");   // staged columns visible to the 8 epilogue warps
 
       mbar_wait(&tmem_full[as], aphase);
@@ -312,12 +314,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         if (col0 >= args.N) break;
         uint32_t raw[32];
         tmem_ld_32x32(tbase + c * 32, raw);
-        if (cc + 1 < CH && col0 + 32 < args.N) epi_prefetch_res<EPI>(args, rnxt, grow, valid, col0 + 32);
+        if (cc + 1 < CH && col0 + 32 < args.N) epi_prefetch_res<EPI, SW>(args, tr, rnxt, col0 + 32, lane);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epi_chunk<EPI>(args, v, sb + c * 32, scs + c * 32, er, rcur, g, nb, h, w, valid, pix, grow, col0, ht_acc);
+        epi_chunk<EPI, SW>(args, v, sb + c * 32, scs + c * 32, stg, tg, er, tr, rcur, col0, lane, ht_acc);
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
       }
@@ -326,6 +328,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
       if (lane == 0) {
         if (leader) mbar_arrive(&tmem_empty[as]);
         else mbar_arrive_remote(&tmem_empty[as], 0);
+      }
+      if constexpr (EPI == EPI_HEADTAIL) {
+        // the row's 4 dot products are split over the two column halves: half 1 hands its partial sums to half 0
+        // through its staging tile (two alternating slots), 64-thread named barrier per lane quadrant (as in gemm.cu)
+        uint8_t* stg_base = reinterpret_cast<uint8_t*>(colv) + Cfg::COLV;
+        float4* slot = reinterpret_cast<float4*>(stg_base + (4 + quad) * Stg<SW>::WARP_BYTES) + (it & 1) * 32;
+        if (half == 1) slot[lane] = make_float4(ht_acc[0], ht_acc[1], ht_acc[2], ht_acc[3]);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+        if (half == 0) {
+          const float4 p = slot[lane];
+          ht_acc[0] += p.x; ht_acc[1] += p.y; ht_acc[2] += p.z; ht_acc[3] += p.w;
+          epi_headtail_finish(args, tg, er, ht_acc);
+        }
       }
     }
   }
@@ -382,8 +397,11 @@ static int launch2_epi(const GemmPlan& plan, cudaStream_t stream) {
     case EPI_PLAIN: return launch2_bn<BN, EPI_PLAIN>(plan, stream);
     case EPI_PIXSHUF: return launch2_bn<BN, EPI_PIXSHUF>(plan, stream);
     case EPI_QKV: return launch2_bn<BN, EPI_QKV>(plan, stream);
+    case EPI_HEADTAIL:
+      if constexpr (BN == 128) return launch2_bn<128, EPI_HEADTAIL>(plan, stream);
+      break;
   }
-  set_error("gemm2_launch: epilogue mode %d is not available on the 2-CTA kernel", plan.args.epi);
+  set_error("gemm2_launch: epilogue mode %d is not available on the 2-CTA kernel at bn %d", plan.args.epi, BN);
   return -1;
 }
 

@@ -1,10 +1,30 @@
-// Fused epilogue of the split-bf16 GEMM engine, shared by the 1-CTA and the 2-CTA (cta_group::2) kernels:
-// one call handles 32 consecutive accumulator columns of one tile row (thread = row).
+// Fused epilogue of the split-bf16 GEMM engine, shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+//
+// Two domains.  tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per chunk): everything that
+// is per column or per row -- folded LayerNorm, bias, activation, RoPE -- is done there.  Global memory is then touched
+// in a TRANSPOSED domain: the warp stages its 32 x 32 chunk in shared memory and re-reads it so that 8 consecutive
+// lanes cover one row's 128 bytes; residual loads, fp32 / split-bf16 stores, LayerNorm statistics and the q / k
+// head-split stores are issued from there.  With thread = row every 16-byte access of a warp hits 32 different cache
+// lines (32 L1 wavefronts per instruction, ~1 us per chunk measured with tools/trace_gemm.py); transposed, an
+// instruction covers 4 whole rows (4 wavefronts).
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
 
 namespace s3r {
+
+// Staging tile of one warp: 32 rows x SW columns (SW = 32, or 16 where shared memory is short: two passes per chunk),
+// row stride SW + 4 floats (16-byte aligned rows, conflict-free for the 128-bit row writes and the transposed reads).
+// Transposed mapping: LPR = SW / 4 lanes per row, 32 / LPR rows per instruction, NIT = LPR instructions per pass.
+template <int SW>
+struct Stg {
+  static constexpr int LD = SW + 4;
+  static constexpr int WARP_BYTES = 32 * LD * 4;
+  static constexpr int LPR = SW / 4;          // lanes per row
+  static constexpr int RPI = 32 / LPR;        // rows per instruction
+  static constexpr int NIT = 32 / RPI;        // instructions per pass (= LPR)
+  static constexpr int NPASS = 32 / SW;       // passes per 32-column chunk
+};
 
 __device__ __forceinline__ void apply_act(float (&v)[32], int act) {
   if (act == ACT_GELU) {
@@ -42,30 +62,76 @@ __device__ __forceinline__ void epi_stage_cols(const GemmArgs& args, float* sb, 
   }
 }
 
-// Per-row state of one tile, loaded before the accumulator wait: LayerNorm statistics of the A row (folded
-// LayerNorm: the GEMM ran on the raw x planes with gamma folded into the weights, the epilogue applies
-// rstd * (acc - mean * colsum) -- identical to LN(x) W^T up to fp32 rounding) and the RoPE position of the row.
-struct EpiRow {
-  float rstd = 1.f, rm = 0.f;   // rm = rstd * mean
-  int py = 0, px = 0;
+// Tile geometry: accumulator row r (0..127) of pixel tile (nb, th, tw) -> pixel (h, w); bw is a power of two.
+struct TileGeom {
+  int g, nb, h0, w0, lbw, bwm;
 };
-template <int EPI>
-__device__ __forceinline__ void epi_row_init(const GemmArgs& args, EpiRow& er, int g, long long pix, long long grow,
-                                             bool valid) {
-  if (args.ln_stats != nullptr && valid) {
-    const int ga = args.a_swap ? (args.groups - 1 - g) : g;
-    // ln_np <= 32 chunk pairs (C <= 1024, even count): all loads are issued before the first add (a rolled loop
-    // would serialise ln_np dependent L2 round trips); fixed summation order
-    const float4* sp = reinterpret_cast<const float4*>(args.ln_stats + ((long long)ga * args.out_group_rows + pix) * args.ln_np);
+__device__ __forceinline__ TileGeom make_geom(const GemmArgs& args, int g, int nb, int th, int tw) {
+  TileGeom t;
+  t.g = g; t.nb = nb; t.h0 = th * args.bh; t.w0 = tw * args.bw;
+  t.lbw = 31 - __clz(args.bw);
+  t.bwm = args.bw - 1;
+  return t;
+}
+__device__ __forceinline__ bool row_pixel(const GemmArgs& args, const TileGeom& t, int r, int& h, int& w, long long& pix) {
+  h = t.h0 + (r >> t.lbw);
+  w = t.w0 + (r & t.bwm);
+  pix = ((long long)t.nb * args.H + h) * args.W + w;   // row inside the group
+  return (h < args.H) && (w < args.W);
+}
+
+// Row-domain state of one thread for one tile.
+struct EpiRow {
+  float rstd = 1.f, rm = 0.f;   // folded LayerNorm: rstd, rstd * mean of the A row
+  int py = 0, px = 0;           // RoPE position of the row (EPI_QKV)
+  bool valid = false;
+  long long pix = 0, grow = 0;  // row inside the group / global output row (EPI_PLAIN)
+  int h = 0, w = 0;
+};
+// Transposed-domain state: lane serves rows rr = it * RPI + lane / LPR, it < NIT (NIT <= 8), four columns each.
+struct EpiTRows {
+  long long key[8];   // PLAIN: global output row; QKV: (gb * heads * ntok + t) * 64; PIXSHUF: h << 32 | w; -1 = no pixel
+};
+
+// Everything that does not need the accumulator; called before the accumulator wait so that its global loads overlap
+// the main loop.  LayerNorm statistics: (sum, sum of squares) per 32-column chunk of the A row, ln_np <= 32 chunks,
+// read cooperatively -- 16 lanes take one row's chunk pairs as float4 (one coalesced 256-byte read per row instead
+// of 16 strided 16-byte reads per thread), two rows per iteration, fixed reduction order.
+template <int EPI, int SW>
+__device__ __forceinline__ void epi_tile_pre(const GemmArgs& args, const TileGeom& tg, int quad, int lane, EpiRow& er,
+                                             EpiTRows& tr) {
+  using S = Stg<SW>;
+  const int r = quad * 32 + lane;
+  er.valid = row_pixel(args, tg, r, er.h, er.w, er.pix);
+  er.grow = (long long)tg.g * args.out_group_rows + er.pix;
+  if (args.ln_stats != nullptr) {
+    const int ga = args.a_swap ? (args.groups - 1 - tg.g) : tg.g;
     const int np2 = args.ln_np >> 1;
-    float4 t[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = (i < np2) ? sp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int sub = lane & 15, half = lane >> 4;
     float s1 = 0.f, s2 = 0.f;
+    float4 t[16];   // all 16 loads are in flight before the first reduction (one L2 round trip, not sixteen)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      s1 += t[i].x + t[i].z;
-      s2 += t[i].y + t[i].w;
+      const int rr = quad * 32 + 2 * i + half;
+      int h2, w2;
+      long long pix2;
+      const bool v2 = row_pixel(args, tg, rr, h2, w2, pix2);
+      t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v2 && sub < np2)
+        t[i] = reinterpret_cast<const float4*>(args.ln_stats + ((long long)ga * args.out_group_rows + pix2) * args.ln_np)[sub];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float a = t[i].x + t[i].z, b = t[i].y + t[i].w;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      const float a0 = __shfl_sync(0xffffffffu, a, 0), a1 = __shfl_sync(0xffffffffu, a, 16);
+      const float b0 = __shfl_sync(0xffffffffu, b, 0), b1 = __shfl_sync(0xffffffffu, b, 16);
+      if (lane == 2 * i) { s1 = a0; s2 = b0; }
+      if (lane == 2 * i + 1) { s1 = a1; s2 = b1; }
     }
     const float inv_c = 1.0f / (float)(args.ln_np * 32);
     const float mean = s1 * inv_c;
@@ -74,35 +140,63 @@ __device__ __forceinline__ void epi_row_init(const GemmArgs& args, EpiRow& er, i
     er.rm = er.rstd * mean;
   }
   if constexpr (EPI == EPI_QKV) {
-    if (args.q_rope && valid) {
-      er.py = args.q_pos[grow * 2];
-      er.px = args.q_pos[grow * 2 + 1];
+    if (args.q_rope && er.valid) {
+      er.py = args.q_pos[er.grow * 2];
+      er.px = args.q_pos[er.grow * 2 + 1];
     }
   }
-}
-
-// Residual rows of the NEXT 32-column chunk, requested while the current chunk is processed (EPI_PLAIN only).
-template <int EPI>
-__device__ __forceinline__ void epi_prefetch_res(const GemmArgs& args, float4 (&rp)[8], long long grow, bool valid,
-                                                 int col0) {
-  if constexpr (EPI == EPI_PLAIN) {
-    if (args.res1 != nullptr && valid) {
-      const float4* p = reinterpret_cast<const float4*>(args.res1 + grow * args.ldr1 + col0);
+  if constexpr (EPI != EPI_HEADTAIL) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rp[q] = p[q];
+    for (int it = 0; it < S::NIT; ++it) {
+      const int rr = quad * 32 + it * S::RPI + lane / S::LPR;
+      int h2, w2;
+      long long pix2;
+      const bool v2 = row_pixel(args, tg, rr, h2, w2, pix2);
+      long long key = -1;
+      if (v2) {
+        if constexpr (EPI == EPI_PLAIN) {
+          key = (long long)tg.g * args.out_group_rows + pix2;
+        } else if constexpr (EPI == EPI_QKV) {
+          const int bidx = (int)(pix2 / args.q_ntok);
+          const int t = (int)(pix2 - (long long)bidx * args.q_ntok);
+          const long long gb = (long long)tg.g * args.q_nb + bidx;
+          key = (gb * (args.q_C >> 6) * args.q_ntok + t) * 64;
+        } else {
+          key = ((long long)h2 << 32) | (unsigned int)w2;
+        }
+      }
+      tr.key[it] = key;
     }
   }
 }
 
-// v: 32 accumulator values (columns col0 .. col0+31 of group g); (nb, h, w): the row's pixel; pix: row index inside the
-// group; grow: global output row for EPI_PLAIN; sb / scs: this chunk's 32 staged bias / colsum values (shared memory);
-// rp: the prefetched res1 values of this chunk (EPI_PLAIN); ht_acc: running 1x1-conv dot products of EPI_HEADTAIL.
-template <int EPI>
+// Residual values of one 32-column chunk in the transposed layout (EPI_PLAIN; requested one chunk ahead).
+template <int EPI, int SW>
+__device__ __forceinline__ void epi_prefetch_res(const GemmArgs& args, const EpiTRows& tr, float4 (&rp)[8], int col0,
+                                                 int lane) {
+  using S = Stg<SW>;
+  if constexpr (EPI == EPI_PLAIN) {
+    if (args.res1 != nullptr) {
+      const int cq = (lane % S::LPR) * 4;
+#pragma unroll
+      for (int p = 0; p < S::NPASS; ++p)
+#pragma unroll
+        for (int it = 0; it < S::NIT; ++it)
+          if (tr.key[it] >= 0)
+            rp[p * S::NIT + it] = *reinterpret_cast<const float4*>(args.res1 + tr.key[it] * args.ldr1 + col0 + p * SW + cq);
+    }
+  }
+}
+
+// One 32-column chunk.  v: this thread's accumulator row; sb / scs: the chunk's staged bias / colsum values; stg: the
+// warp's staging tile; rp: prefetched residual (transposed layout); ht_acc: running dot products of EPI_HEADTAIL.
+template <int EPI, int SW>
 __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], const float* sb, const float* scs,
-                                          const EpiRow& er, const float4 (&rp)[8], int g, int nb, int h, int w,
-                                          bool valid, long long pix, long long grow, int col0, float (&ht_acc)[4]) {
+                                          float* stg, const TileGeom& tg, const EpiRow& er, const EpiTRows& tr,
+                                          const float4 (&rp)[8], int col0, int lane, float (&ht_acc)[4]) {
+  // ---------------------------------------------------------------- row domain
   if (args.ln_stats != nullptr) {
-    const float4* c4 = reinterpret_cast<const float4*>(scs);   // 128-byte aligned chunk of the staged columns
+    const float4* c4 = reinterpret_cast<const float4*>(scs);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 c = c4[q];
@@ -125,129 +219,8 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
   }
   if (args.act != ACT_NONE) apply_act(v, args.act);
 
-  if constexpr (EPI == EPI_PLAIN || EPI == EPI_PIXSHUF) {
-    long long orow = grow;
-    int ocol = col0;
-    if constexpr (EPI == EPI_PIXSHUF) {
-      const int ij = col0 / args.ps_cout;
-      ocol = col0 - ij * args.ps_cout;
-      const int s = args.ps_s;
-      const int i = ij / s, j = ij - i * s;
-      orow = (long long)g * args.out_group_rows +
-             ((long long)nb * (args.H * s) + (h * s + i)) * (args.W * s) + (w * s + j);
-    }
-    if (valid) {
-      if (args.res1 != nullptr) {
-        if constexpr (EPI == EPI_PLAIN) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            v[4 * q + 0] += rp[q].x;
-            v[4 * q + 1] += rp[q].y;
-            v[4 * q + 2] += rp[q].z;
-            v[4 * q + 3] += rp[q].w;
-          }
-        } else {
-          const float4* r1 = reinterpret_cast<const float4*>(args.res1 + orow * args.ldr1 + ocol);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 t = r1[q];
-            v[4 * q + 0] += t.x;
-            v[4 * q + 1] += t.y;
-            v[4 * q + 2] += t.z;
-            v[4 * q + 3] += t.w;
-          }
-        }
-      }
-      if (args.res2 != nullptr) {
-        const float4* r2 = reinterpret_cast<const float4*>(args.res2 + orow * args.ldr2 + ocol);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = r2[q];
-          v[4 * q + 0] += t.x;
-          v[4 * q + 1] += t.y;
-          v[4 * q + 2] += t.z;
-          v[4 * q + 3] += t.w;
-        }
-      }
-      if constexpr (EPI == EPI_PLAIN) {
-        if (args.stats_out != nullptr) {   // (sum, sum of squares) of this row over the chunk: LayerNorm statistics
-          float s1 = 0.f, s2 = 0.f;         // of the residual stream for the NEXT GEMM's folded LayerNorm
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            s1 += v[j];
-            s2 = fmaf(v[j], v[j], s2);
-          }
-          args.stats_out[orow * (long long)(args.N >> 5) + (col0 >> 5)] = make_float2(s1, s2);
-        }
-      }
-      if (args.out_f32 != nullptr) {
-        float* op = args.out_f32 + orow * args.ldo + ocol;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) st_f4(op + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-      if (args.out_hi != nullptr) {
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float a = v[2 * q], b = v[2 * q + 1];
-          if (args.plane_relu) {
-            a = fmaxf(a, 0.f);
-            b = fmaxf(b, 0.f);
-          }
-          split2_bf16(a, b, ph[q], pl[q]);
-        }
-        const long long po = orow * args.ldp + args.plane_col0 + ocol;
-        uint4* hp = reinterpret_cast<uint4*>(args.out_hi + po);
-        uint4* lp = reinterpret_cast<uint4*>(args.out_lo + po);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          hp[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-          lp[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-        }
-      }
-    }
-  } else if constexpr (EPI == EPI_QKV) {
-    // croco/models/blocks.py:97-104 (self) / :154-160 (cross) + RoPE2D (pos_embed.py:112-159,
-    // curope/kernels.cu:18-81): head dim 64 = [y half | x half], each half = 16 (u, v) pairs
-    // (j, j+16) rotated by pos * 100^(-j/16).
-    const int role = args.q_role_base + col0 / args.q_C;  // 0 q, 1 k, 2 v
-    const int cc = col0 % args.q_C;
-    const int head = cc >> 6;
-    const int d0 = cc & 63;  // 0 or 32
-    const int heads = args.q_C >> 6;
-    const int bidx = (int)(pix / args.q_ntok);
-    const int t = (int)(pix - (long long)bidx * args.q_ntok);
-    const long long gb = (long long)g * args.q_nb + bidx;
-    if (valid) {
-      if (role <= 1 && args.q_rope) {
-        const int p = (d0 >> 5) ? er.px : er.py;
-        const float2* cs = args.q_cs + p * 16;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 t2 = __ldg(cs + j);
-          const float u = v[j], x = v[j + 16];
-          v[j] = u * t2.x - x * t2.y;
-          v[j + 16] = x * t2.x + u * t2.y;
-        }
-      }
-      if (role == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= args.q_scale;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = to_tf32(v[j]);
-      if (role <= 1) {
-        float* op = (role == 0 ? args.q_out : args.k_out) + ((gb * heads + head) * args.q_ntok + t) * 64 + d0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) st_f4(op + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      } else {
-        float* op = args.vt_out + ((gb * heads + head) * 64 + d0) * (long long)args.q_ntok_pad + t;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) op[(long long)j * args.q_ntok_pad] = v[j];
-      }
-    }
-  } else {  // EPI_HEADTAIL: dpt_block.py:318-324 (ReLU, 1x1 conv) + heads/postprocess.py:10-58
-    const float* wt = args.ht_w + (long long)g * 4 * 128 + col0;
+  if constexpr (EPI == EPI_HEADTAIL) {   // dpt_block.py:318-324 (ReLU, 1x1 conv) + heads/postprocess.py:10-58
+    const float* wt = args.ht_w + (long long)tg.g * 4 * 128 + col0;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       const float4* wp = reinterpret_cast<const float4*>(wt + o * 128);
@@ -262,7 +235,157 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
       }
       ht_acc[o] = acc;
     }
+    return;
   }
+
+  int role = 0, head = 0, d0 = 0;
+  if constexpr (EPI == EPI_QKV) {
+    // croco/models/blocks.py:97-104 (self) / :154-160 (cross) + RoPE2D (pos_embed.py:112-159,
+    // curope/kernels.cu:18-81): head dim 64 = [y half | x half], each half = 16 (u, v) pairs
+    // (j, j+16) rotated by pos * 100^(-j/16).
+    role = args.q_role_base + col0 / args.q_C;  // 0 q, 1 k, 2 v
+    const int cc = col0 % args.q_C;
+    head = cc >> 6;
+    d0 = cc & 63;  // 0 or 32
+    if (role <= 1 && args.q_rope) {
+      const int p = (d0 >> 5) ? er.px : er.py;
+      const float2* cs = args.q_cs + p * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 t2 = __ldg(cs + j);
+        const float u = v[j], x = v[j + 16];
+        v[j] = u * t2.x - x * t2.y;
+        v[j + 16] = x * t2.x + u * t2.y;
+      }
+    }
+    if (role == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= args.q_scale;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = to_tf32(v[j]);
+    if (role == 2) {   // V^T: for a fixed column the warp's 32 rows are 32 consecutive tokens -> already coalesced
+      if (er.valid) {
+        const int heads = args.q_C >> 6;
+        const int bidx = (int)(er.pix / args.q_ntok);
+        const int t = (int)(er.pix - (long long)bidx * args.q_ntok);
+        const long long gb = (long long)tg.g * args.q_nb + bidx;
+        float* op = args.vt_out + ((gb * heads + head) * 64 + d0) * (long long)args.q_ntok_pad + t;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) op[(long long)j * args.q_ntok_pad] = v[j];
+      }
+      return;
+    }
+  }
+
+  // ---------------------------------------------------------------- stage, then transposed domain
+  using S = Stg<SW>;
+  const int cq = (lane % S::LPR) * 4;
+  const int lr = lane / S::LPR;
+  int ocol0 = col0;
+  int ps_i = 0, ps_j = 0;
+  if constexpr (EPI == EPI_PIXSHUF) {
+    const int ij = col0 / args.ps_cout;
+    ocol0 = col0 - ij * args.ps_cout;
+    ps_i = ij / args.ps_s;
+    ps_j = ij - ps_i * args.ps_s;
+  }
+  float st1[S::NIT], st2[S::NIT];   // LayerNorm statistics of the chunk, accumulated over the passes
+#pragma unroll
+  for (int it = 0; it < S::NIT; ++it) st1[it] = st2[it] = 0.f;
+#pragma unroll
+  for (int p = 0; p < S::NPASS; ++p) {
+    {
+      float4* sp = reinterpret_cast<float4*>(stg + lane * S::LD);
+#pragma unroll
+      for (int q = 0; q < SW / 4; ++q) {
+        const int j = p * SW + 4 * q;
+        sp[q] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    __syncwarp();
+    const int ocol = ocol0 + p * SW + cq;
+#pragma unroll
+    for (int it = 0; it < S::NIT; ++it) {
+      const long long key = tr.key[it];
+      float4 x = *reinterpret_cast<const float4*>(stg + (it * S::RPI + lr) * S::LD + cq);
+      if constexpr (EPI == EPI_QKV) {
+        if (key >= 0) {
+          float* op = (role == 0 ? args.q_out : args.k_out) + key + (long long)head * args.q_ntok * 64 + d0 + p * SW + cq;
+          *reinterpret_cast<float4*>(op) = x;
+        }
+      } else {
+        long long orow = key;
+        if constexpr (EPI == EPI_PIXSHUF) {
+          if (key >= 0) {
+            const int s = args.ps_s;
+            const int h = (int)(key >> 32), w = (int)(key & 0xffffffffLL);
+            orow = (long long)tg.g * args.out_group_rows +
+                   ((long long)tg.nb * (args.H * s) + (h * s + ps_i)) * (args.W * s) + (w * s + ps_j);
+          }
+        }
+        const bool ok = key >= 0;
+        if (ok) {
+          if (args.res1 != nullptr) {
+            float4 t;
+            if constexpr (EPI == EPI_PLAIN) t = rp[p * S::NIT + it];
+            else t = *reinterpret_cast<const float4*>(args.res1 + orow * args.ldr1 + ocol);
+            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+          }
+          if (args.res2 != nullptr) {
+            const float4 t = *reinterpret_cast<const float4*>(args.res2 + orow * args.ldr2 + ocol);
+            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+          }
+        }
+        if constexpr (EPI == EPI_PLAIN) {
+          if (args.stats_out != nullptr) {   // (sum, sum of squares) of the row over this chunk: LayerNorm statistics
+            st1[it] += (x.x + x.y) + (x.z + x.w);   // of the residual stream for the NEXT GEMM's folded LayerNorm
+            st2[it] += fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+            if (p == S::NPASS - 1) {
+              float s1 = st1[it], s2 = st2[it];
+#pragma unroll
+              for (int o = 1; o < S::LPR; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              }
+              if (ok && (lane % S::LPR) == 0)
+                args.stats_out[orow * (long long)(args.N >> 5) + (col0 >> 5)] = make_float2(s1, s2);
+            }
+          }
+        }
+        if (ok) {
+          if (args.out_f32 != nullptr) *reinterpret_cast<float4*>(args.out_f32 + orow * args.ldo + ocol) = x;
+          if (args.out_hi != nullptr) {
+            if (args.plane_relu) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            }
+            uint32_t h0, l0, h1, l1;
+            split2_bf16(x.x, x.y, h0, l0);
+            split2_bf16(x.z, x.w, h1, l1);
+            const long long po = orow * args.ldp + args.plane_col0 + ocol;
+            *reinterpret_cast<uint2*>(args.out_hi + po) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(args.out_lo + po) = make_uint2(l0, l1);
+          }
+        }
+      }
+    }
+    __syncwarp();   // the staging tile is rewritten by the next pass / chunk
+  }
+}
+
+// EPI_HEADTAIL: after the last chunk, the row's 4 dot products -> pts3d / conf (heads/postprocess.py:10-58)
+__device__ __forceinline__ void epi_headtail_finish(const GemmArgs& args, const TileGeom& tg, const EpiRow& er,
+                                                    const float (&ht_acc)[4]) {
+  if (!er.valid) return;
+  const float* b4 = args.ht_b + tg.g * 4;
+  const float x = ht_acc[0] + b4[0], y = ht_acc[1] + b4[1], z = ht_acc[2] + b4[2], cf = ht_acc[3] + b4[3];
+  const float d = sqrtf(x * x + y * y + z * z);
+  const float sc = expm1f(d) / fmaxf(d, 1e-8f);
+  float* pp = args.ht_pts + er.grow * 3;
+  pp[0] = x * sc;
+  pp[1] = y * sc;
+  pp[2] = z * sc;
+  args.ht_conf[er.grow] = 1.0f + expf(cf);
 }
 
 }  // namespace s3r

@@ -199,8 +199,11 @@ def test_cross_attention_shapes(L):
     assert rel_l2(o, ref) < TOL_ATTN, rel_l2(o, ref)
 
 
-def test_head_tail(L):
-    groups, NB, H, W, Cin = 2, 1, 48, 64, 128
+@pytest.mark.parametrize("H,W,bn", [(48, 64, 0), (48, 64, 128), (24, 40, 0), (96, 128, 0)])
+def test_head_tail(L, H, W, bn):
+    """bn 0: the planner's choice (256 x 128 CTA-pair tiles where the pixel-tile count is even, the two column halves'
+    partial dot products meet in shared memory), 128: the 1-CTA kernel."""
+    groups, NB, Cin = 2, 1, 128
     x = _rand(groups * NB, Cin, H, W, seed=30)
     w = _rand(groups * 128, Cin, 3, 3, seed=31, scale=(9 * Cin) ** -0.5)
     b = _rand(groups * 128, seed=32, scale=0.1)
@@ -213,7 +216,7 @@ def test_head_tail(L):
     d = L.GemmDesc()
     d.a_hi, d.a_lo, d.b_hi, d.b_lo = xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr()
     d.groups, d.nb, d.h, d.w, d.kc, d.taps, d.n = groups, NB, H, W, Cin, 9, 128
-    d.epi, d.act = L.EPI_HEADTAIL, L.ACT_RELU
+    d.epi, d.act, d.force_bn = L.EPI_HEADTAIL, L.ACT_RELU, bn
     d.bias = b.data_ptr()
     d.ht_w, d.ht_b, d.ht_pts, d.ht_conf = w4.data_ptr(), b4.data_ptr(), pts.data_ptr(), conf.data_ptr()
     L.gemm(d)

@@ -46,17 +46,25 @@ for name, H, W, Cin, Cout, taps, mode in SHAPES:
         d.out_hi, d.out_lo, d.ldp, d.plane_relu = oh.data_ptr(), ol.data_ptr(), Cout, 1
     else:
         d.out_f32, d.ldo = out.data_ptr(), Cout
-    for _ in range(3):
-        L.gemm(d)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 20
-    e0.record()
-    for _ in range(iters):
-        L.gemm(d)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / iters * 1e3
-    tf = 2.0 * G * H * W * Cout * Cin * taps / us / 1e6
-    bn = L.lib().s3r_gemm_tile_n(d)
-    print(f"{name:14s} {H:3d}x{W:<4d} {Cin:4d}->{Cout:<4d} taps{taps} {mode:6s} bn{bn:<3d}: {us:8.1f} us {tf:6.1f} TF", flush=True)
+    res_txt = []
+    sweep = [0] + ([b for b in (64, 128, 256, 2128, 2256) if (b % 1000) <= Cout] if "--sweep" in sys.argv else [])
+    for fb in sweep:
+        d.force_bn = fb
+        try:
+            for _ in range(3):
+                L.gemm(d)
+        except Exception:
+            continue
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for _ in range(iters):
+            L.gemm(d)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        bn = L.lib().s3r_gemm_tile_n(d)
+        res_txt.append(f"{'auto' if fb == 0 else fb}(bn{bn}) {us:7.1f}us")
+    tf = 2.0 * G * H * W * Cout * Cin * taps / 1e6
+    print(f"{name:14s} {H:3d}x{W:<4d} {Cin:4d}->{Cout:<4d} taps{taps} {mode:6s} " + " | ".join(res_txt) + f"   [{tf:.0f} MFLOP]", flush=True)
