@@ -415,6 +415,16 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   if (c128 < c64) bn = 128;
   if (c2128 <= (bn == 64 ? c64 : c128)) { bn = 128; two = 1; }
   if (N <= 64) { bn = 64; two = 0; }
+  // many-wave GEMMs whose width is a multiple of 256 (the batched encoder): 256 x 256 pair tiles halve the number of
+  // per-tile epilogue preambles (LayerNorm statistics, staged columns) -- measured in situ, not visible in the sweep
+  static const int p2256 = getenv("S3R_P2256") ? atoi(getenv("S3R_P2256")) : 1;
+  static const int small2 = getenv("S3R_SMALL2") ? atoi(getenv("S3R_SMALL2")) : 1;
+  const long long tiles128 = m_tiles * nt128;
+  if (p2256 && two && taps == 1 && N % 256 == 0 && tiles128 >= 400) bn = 256;
+  if (!small2 && two && tiles128 < 400 && taps == 1) {   // experiment: 1-CTA tiles for the single-wave linears
+    two = 0;
+    bn = (c128 < c64) ? 128 : 64;
+  }
   if (force_bn == 0 && legal2 && (g2_mode == 128 || g2_mode == 256)) {
     two = 1;
     bn = (g2_mode == 256 && N % 256 == 0) ? 256 : 128;
