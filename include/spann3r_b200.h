@@ -111,6 +111,10 @@ typedef struct s3r_gemm_desc {
   /* diagnostics: 16 x uint64 %globaltimer stamps of CTA 0 (entry, prologue done, dependency wait done, first operands
    * landed, accumulator ready, epilogue done, exit, ...; tools/trace_gemm.py); NULL = off.  1-CTA kernel only. */
   uint64_t* trace;
+  /* merged projections: a_swap applies to output columns >= swap_col0 only (0 = all; a multiple of 256), and EPI_QKV
+   * roles 3 / 4 (columns 3*q_c .. 5*q_c) are a second K / V^T pair written to k2_out / vt2_out -- the decoder's
+   * self-attention qkv and cross-attention k, v projections (croco/models/blocks.py:186-189) as ONE launch */
+  int swap_col0; float* k2_out; float* vt2_out;
 } s3r_gemm_desc;
 int s3r_gemm(const s3r_gemm_desc* d, void* stream);
 /* tile width the planner would pick (64/128/256), for tests */
@@ -143,8 +147,9 @@ typedef struct s3r_lin { s3r_planes w; const float* b; const float* cs; } s3r_li
 typedef struct s3r_block_w {       /* croco/models/blocks.py:114-130 */
   s3r_ln norm1; s3r_lin qkv; s3r_lin proj; s3r_ln norm2; s3r_lin fc1; s3r_lin fc2;
 } s3r_block_w;
-typedef struct s3r_decblock_w {    /* croco/models/blocks.py:171-191, two streams as 2 groups; kv = [projk; projv] */
-  s3r_ln norm1; s3r_lin qkv; s3r_lin proj; s3r_ln norm_y; s3r_ln norm2; s3r_lin q; s3r_lin kv; s3r_lin cproj;
+typedef struct s3r_decblock_w {    /* croco/models/blocks.py:171-191, two streams as 2 groups */
+  /* qkv: per group [attn.qkv (norm1 folded); cross_attn.projk; cross_attn.projv (norm_y folded)], N = 5 * 768 */
+  s3r_ln norm1; s3r_lin qkv; s3r_lin proj; s3r_ln norm_y; s3r_ln norm2; s3r_lin q; s3r_lin cproj;
   s3r_ln norm3; s3r_lin fc1; s3r_lin fc2;
 } s3r_decblock_w;
 typedef struct s3r_rcu_w { s3r_lin conv1; s3r_lin conv2; } s3r_rcu_w;                 /* dpt_block.py:121-142 */

@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("ln_stats", _vp), ("ln_np", _i), ("ln_eps", _f), ("ln_cs", _vp), ("a_swap", _i),
         ("stats_out", _vp),
         ("trace", _vp),
+        ("swap_col0", _i), ("k2_out", _vp), ("vt2_out", _vp),
     ]
 
 

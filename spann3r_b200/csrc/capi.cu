@@ -102,6 +102,7 @@ static int fill_plan(const s3r_gemm_desc* d, GemmPlan* plan) {
     a.q_rope = d->q_rope; a.q_nb = d->q_nb; a.q_pos = d->q_pos;
     a.q_cs = reinterpret_cast<const float2*>(d->q_cs);
     a.q_out = d->q_out; a.k_out = d->k_out; a.vt_out = d->vt_out; a.q_scale = d->q_scale;
+    a.k2_out = d->k2_out; a.vt2_out = d->vt2_out;
   }
   if (d->epi == S3R_EPI_HEADTAIL) {
     a.ht_w = d->ht_w; a.ht_b = d->ht_b; a.ht_pts = d->ht_pts; a.ht_conf = d->ht_conf;
@@ -114,6 +115,11 @@ static int fill_plan(const s3r_gemm_desc* d, GemmPlan* plan) {
     a.ln_stats = reinterpret_cast<const float2*>(d->ln_stats); a.ln_np = d->ln_np; a.ln_eps = d->ln_eps; a.ln_cs = d->ln_cs;
   }
   a.a_swap = d->a_swap ? 1 : 0;
+  if (d->swap_col0 % 256 != 0) {
+    set_error("s3r_gemm: swap_col0 must be a multiple of 256");
+    return -1;
+  }
+  a.swap_col0 = d->swap_col0;
   if (d->stats_out) {
     if (d->epi != S3R_EPI_PLAIN || d->n % 32 != 0) {
       set_error("s3r_gemm: stats_out needs EPI_PLAIN and n %% 32 == 0");

@@ -48,6 +48,7 @@ struct Epi {
   int q_C = 0, q_role_base = 0, q_ntok = 0, q_ntok_pad = 0, q_rope = 0, q_nb = 0;
   const int* q_pos = nullptr; const float2* q_cs = nullptr;
   float *q_out = nullptr, *k_out = nullptr, *vt_out = nullptr; float q_scale = 1.f;
+  float *k2_out = nullptr, *vt2_out = nullptr; int swap_col0 = 0;
   const float *ht_w = nullptr, *ht_b = nullptr; float *ht_pts = nullptr, *ht_conf = nullptr;
   // folded LayerNorm: consumer side (statistics of the A rows + column sums of the gamma-folded weights) ...
   const float2* ln_stats = nullptr; int ln_np = 0; float ln_eps = 0.f; const float* ln_cs = nullptr; int a_swap = 0;
@@ -104,6 +105,7 @@ struct s3r_engine {
   // decoder workspace (2 groups x R rows, dim 768)
   float2 *Sa = nullptr, *Sb = nullptr, *Sc = nullptr;
   float* Xd = nullptr; Planes Pa, Pb, Pc, AOd, Hd, E0, Hk6, Hk9, Hk12, KH, KHh; float *Qd = nullptr, *Kd = nullptr, *Vtd = nullptr;
+  float *Kd2 = nullptr, *Vtd2 = nullptr;   // cross-attention K / V^T (written by the merged qkv launch, read after self attention)
   float* D12 = nullptr; float* KO = nullptr;
   // DPT workspace
   Planes T1, T2, T4, T4c, A1, A2, A3, A4;       // act_postprocess stages
@@ -114,6 +116,10 @@ struct s3r_engine {
   float* Xv = nullptr; Planes Pv;
   // memory read
   Planes Qn, Pm; float* Sm = nullptr; float* ln_tmp = nullptr; float* sim_scratch = nullptr; int mem_cap = 0;
+
+  // side streams of the DPT heads: the four act_postprocess -> layer_rn chains are independent until refinenet4
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 
   std::map<int, PlanCache> pc_encode;  // keyed by nimg
   PlanCache pc_decode, pc_keys, pc_heads, pc_value;
@@ -162,10 +168,12 @@ struct s3r_engine {
       a.q_C = e.q_C; a.q_role_base = e.q_role_base; a.q_ntok = e.q_ntok; a.q_ntok_pad = e.q_ntok_pad;
       a.q_rope = e.q_rope; a.q_nb = e.q_nb; a.q_pos = e.q_pos; a.q_cs = e.q_cs;
       a.q_out = e.q_out; a.k_out = e.k_out; a.vt_out = e.vt_out; a.q_scale = e.q_scale;
+      a.k2_out = e.k2_out; a.vt2_out = e.vt2_out;
     } else if (e.epi == EPI_HEADTAIL) {
       a.ht_w = e.ht_w; a.ht_b = e.ht_b; a.ht_pts = e.ht_pts; a.ht_conf = e.ht_conf;
     }
     a.ln_stats = e.ln_stats; a.ln_np = e.ln_np; a.ln_eps = e.ln_eps; a.ln_cs = e.ln_cs; a.a_swap = e.a_swap;
+    a.swap_col0 = e.swap_col0;
     a.stats_out = e.stats_out;
     flops += p.flops;
     ++launches;
@@ -318,6 +326,8 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
   e->Qd = e->alloc<float>(2 * R * 768);
   e->Kd = e->alloc<float>(2 * R * 768);
   e->Vtd = e->alloc<float>((size_t)2 * batch * 12 * 64 * e->Npad);
+  e->Kd2 = e->alloc<float>(2 * R * 768);
+  e->Vtd2 = e->alloc<float>((size_t)2 * batch * 12 * 64 * e->Npad);
   e->D12 = e->alloc<float>(2 * R * 768);
   e->KO = e->alloc<float>(2 * R * 1024);
   // DPT (2 heads as groups, batch images each)
@@ -354,6 +364,14 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
   e->Qn = e->alloc_planes(R * 1024);
   e->ln_tmp = e->alloc<float>(R * 1024);
   e->sim_scratch = e->alloc<float>((size_t)batch * 8 * N + 64);
+  for (int i = 0; i < 3 && !e->status; ++i) {
+    if (cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      set_error("s3r_engine_create: side stream / event creation failed");
+      e->status = -7;
+    }
+  }
+  if (!e->status && cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) e->status = -7;
   if (e->status) {
     s3r_engine_destroy(e);
     return nullptr;
@@ -370,6 +388,11 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
 void s3r_engine_destroy(s3r_engine* e) {
   if (!e) return;
   for (void* p : e->allocs) cudaFree(p);
+  for (int i = 0; i < 3; ++i) {
+    if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   delete e;
 }
 
@@ -488,13 +511,14 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
   Planes xin = e->Pa;
   for (int l = 0; l < 12; ++l) {
     const s3r_decblock_w& bw = e->w.dec[l];
-    // self attention
+    // self-attention q, k, v (norm1 folded) and -- same launch, columns >= 2304 reading the OTHER stream's layer
+    // input (norm_y folded, group swap) -- the cross-attention k, v
     {
-      Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 2304;
+      Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 3840;
       Epi ep; ep.epi = EPI_QKV; ep.bias = bw.qkv.b; ep.q_C = 768; ep.q_role_base = 0; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
       ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
-      ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.q_scale = 0.125f;
-      ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.qkv.cs;                      // norm1
+      ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.k2_out = e->Kd2; ep.vt2_out = e->Vtd2; ep.q_scale = 0.125f;
+      ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.qkv.cs; ep.a_swap = 1; ep.swap_col0 = 2304;
       if ((r = e->gemm(pc, xin, WP(bw.qkv.w), g, ep, st))) return r;
     }
     if ((r = e->attention(pc, e->Qd, e->Kd, e->Vtd, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
@@ -513,15 +537,7 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
       ep.ln_stats = e->Sb; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.q.cs;                        // norm2
       if ((r = e->gemm(pc, e->Pb, WP(bw.q.w), g, ep, st))) return r;
     }
-    {
-      Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 1536;
-      Epi ep; ep.epi = EPI_QKV; ep.bias = bw.kv.b; ep.q_C = 768; ep.q_role_base = 1; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
-      ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
-      ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.q_scale = 0.125f;
-      ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.kv.cs; ep.a_swap = 1;        // norm_y
-      if ((r = e->gemm(pc, xin, WP(bw.kv.w), g, ep, st))) return r;
-    }
-    if ((r = e->attention(pc, e->Qd, e->Kd, e->Vtd, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
+    if ((r = e->attention(pc, e->Qd, e->Kd2, e->Vtd2, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 768;
       Epi ep; ep.bias = bw.cproj.b; ep.res1 = e->Xd; ep.ldr1 = 768; ep.out = e->Xd; ep.ldo = 768;
@@ -607,34 +623,60 @@ int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
   const int B = e->B, gh = e->gh, gw = e->gw;
   const int h3 = (gh + 1) / 2, w3 = (gw + 1) / 2;
   int r;
+  cudaStream_t cur = st;   // stream the next launch goes to
   auto conv1x1 = [&](Planes A, int H, int W, int Cin, const s3r_lin& w, int Cout, Epi ep) {
     Geom g; g.groups = 2; g.NB = B; g.H = H; g.W = W; g.Kc = Cin; g.N = Cout;
     ep.bias = w.b;
-    return e->gemm(pc, A, WP(w.w), g, ep, st);
+    return e->gemm(pc, A, WP(w.w), g, ep, cur);
   };
   auto conv3x3 = [&](Planes A, int H, int W, int Cin, const s3r_lin& w, int Cout, Epi ep) {
     Geom g; g.groups = 2; g.NB = B; g.H = H; g.W = W; g.Kc = Cin; g.taps = 9; g.N = Cout;
     ep.bias = w.b;
-    return e->gemm(pc, A, WP(w.w), g, ep, st);
+    return e->gemm(pc, A, WP(w.w), g, ep, cur);
   };
-  // --- act_postprocess (dpt_block.py:356-410) ---
+  const int LH[4] = {4 * gh, 2 * gh, gh, h3}, LW[4] = {4 * gw, 2 * gw, gw, w3}, LC[4] = {96, 192, 384, 768};
+  Planes Lin[4] = {e->A1, e->A2, e->A3, e->A4};
+  auto layer_rn = [&](int i) {   // layer_rn (3x3, no bias): fp32 (residual) + relu planes (next conv's input)
+    Epi ep; ep.out = e->Lf[i]; ep.ldo = 256; ep.op = e->Lr[i]; ep.ldp = 256; ep.plane_relu = 1;
+    return conv3x3(Lin[i], LH[i], LW[i], LC[i], d.layer_rn[i], 256, ep);
+  };
+  // --- act_postprocess (dpt_block.py:356-410) + layer_rn (:33-75): four chains, one per pyramid level, independent
+  // until refinenet4.  They are small (2 .. 96 pixel tiles) and latency-bound, so levels 2-4 run on side streams
+  // beside level 1 (forked / joined with events; single stream while per-launch profiling is on).  The launch ORDER
+  // in the plan cache is the same either way.
+  const bool par = !e->profiling;
+  if (par) {
+    cudaEventRecord(e->ev_fork, st);
+    for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(e->side[i], e->ev_fork, 0);
+  }
+  // level 1 (4gh x 4gw)
   { Epi ep; ep.op = e->T1; ep.ldp = 96; if ((r = conv1x1(e->E0, gh, gw, 1024, d.act1_conv, 96, ep))) return r; }
   { Epi ep; ep.epi = EPI_PIXSHUF; ep.ps_s = 4; ep.ps_cout = 96; ep.op = e->A1; ep.ldp = 96;
     if ((r = conv1x1(e->T1, gh, gw, 96, d.act1_up, 16 * 96, ep))) return r; }
+  if ((r = layer_rn(0))) return r;
+  // level 2 (2gh x 2gw)
+  if (par) cur = e->side[0];
   { Epi ep; ep.op = e->T2; ep.ldp = 192; if ((r = conv1x1(e->Hk6, gh, gw, 768, d.act2_conv, 192, ep))) return r; }
   { Epi ep; ep.epi = EPI_PIXSHUF; ep.ps_s = 2; ep.ps_cout = 192; ep.op = e->A2; ep.ldp = 192;
     if ((r = conv1x1(e->T2, gh, gw, 192, d.act2_up, 4 * 192, ep))) return r; }
+  if ((r = layer_rn(1))) return r;
+  // level 3 (gh x gw)
+  if (par) cur = e->side[1];
   { Epi ep; ep.op = e->A3; ep.ldp = 384; if ((r = conv1x1(e->Hk9, gh, gw, 768, d.act3_conv, 384, ep))) return r; }
+  if ((r = layer_rn(2))) return r;
+  // level 4 (gh/2 x gw/2): 1x1, then the stride-2 3x3 as im2col + GEMM
+  if (par) cur = e->side[2];
   { Epi ep; ep.op = e->T4; ep.ldp = 768; if ((r = conv1x1(e->Hk12, gh, gw, 768, d.act4_conv, 768, ep))) return r; }
   ++e->launches;
-  if ((r = launch_im2col_3x3s2(e->T4.hi, e->T4.lo, 2 * B, gh, gw, 768, h3, w3, e->T4c.hi, e->T4c.lo, st))) return r;
+  if ((r = launch_im2col_3x3s2(e->T4.hi, e->T4.lo, 2 * B, gh, gw, 768, h3, w3, e->T4c.hi, e->T4c.lo, cur))) return r;
   { Epi ep; ep.op = e->A4; ep.ldp = 768; if ((r = conv1x1(e->T4c, h3, w3, 9 * 768, d.act4_down, 768, ep))) return r; }
-  // --- layer_rn (3x3, no bias): fp32 (residual) + relu planes (next conv's input) ---
-  const int LH[4] = {4 * gh, 2 * gh, gh, h3}, LW[4] = {4 * gw, 2 * gw, gw, w3}, LC[4] = {96, 192, 384, 768};
-  Planes Lin[4] = {e->A1, e->A2, e->A3, e->A4};
-  for (int i = 0; i < 4; ++i) {
-    Epi ep; ep.out = e->Lf[i]; ep.ldo = 256; ep.op = e->Lr[i]; ep.ldp = 256; ep.plane_relu = 1;
-    if ((r = conv3x3(Lin[i], LH[i], LW[i], LC[i], d.layer_rn[i], 256, ep))) return r;
+  if ((r = layer_rn(3))) return r;
+  cur = st;
+  if (par) {
+    for (int i = 0; i < 3; ++i) {
+      cudaEventRecord(e->ev_join[i], e->side[i]);
+      cudaStreamWaitEvent(st, e->ev_join[i], 0);
+    }
   }
   // --- refinenet4 .. refinenet1 (FeatureFusionBlock_custom, dpt_block.py:189-218) ---
   const float* path = nullptr;  // fp32 path from the coarser level, at this level's resolution

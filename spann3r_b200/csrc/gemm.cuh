@@ -45,6 +45,7 @@ struct GemmArgs {
   const float2* ln_stats; int ln_np; float ln_eps;
   const float* ln_cs;                 // [G*N] column sums of W' (as the tensor core sees it: hi + lo planes)
   int a_swap;                         // 1: group g reads the A rows (and statistics) of group G-1-g (norm_y of the twin decoders)
+  int swap_col0;                      // ... for output columns >= swap_col0 only (0 = all); must be a multiple of the tile width
   // Producer side (EPI_PLAIN): write (sum, sum of squares) of every output row chunk, [rows, N/32]
   float2* stats_out;
   // optional timeline of CTA 0 (tools/trace_gemm.py): 8 x %globaltimer stamps, null = off
@@ -56,6 +57,7 @@ struct GemmArgs {
   const int* q_pos;        // [G*rows, 2] (y, x) per A row
   const float2* q_cs;      // [maxpos, 16] (cos, sin)
   float* q_out; float* k_out; float* vt_out;
+  float* k2_out; float* vt2_out;       // roles 3 / 4: a second K / V^T pair (the cross-attention K/V of the merged decoder launch)
   float q_scale;
   // L2 prefetch of the NEXT GEMM's weight planes (static data): issued by the idle epilogue warps at kernel start so
   // that the next kernel's first touch of its weights hits L2 instead of HBM (small-M GEMMs are latency bound)

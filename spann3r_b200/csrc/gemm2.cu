@@ -185,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         const int th = (mt / args.tiles_w) % args.tiles_h;
         const int nb = mt / (args.tiles_w * args.tiles_h);
         const int w0 = tw * args.bw, h0 = th * args.bh;
-        const int img = (args.a_swap ? (args.groups - 1 - g) : g) * args.NB + nb;
+        const int img = ((args.a_swap && nt * BN >= args.swap_col0) ? (args.groups - 1 - g) : g) * args.NB + nb;
         const int brow = g * args.b_group_rows + nt * BN + (int)rank * (BN / 2);
         int tap = 0, kc = 0, dx = (args.taps == 9) ? -1 : 0, dy = dx;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -294,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
       float* scs = sb + BN;
       float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(colv) + Cfg::COLV + (warp - 2) * Stg<SW>::WARP_BYTES);
       epi_stage_cols<EPI, BN>(args, sb, scs, g, nt, (int)threadIdx.x - 64, 32 * kEpiWarps);
-      const TileGeom tg = make_geom(args, g, nb, th, tw);
+      const TileGeom tg = make_geom(args, g, nb, th, tw, nt * BN);
       EpiRow er;
       EpiTRows tr;
       epi_tile_pre<EPI, SW>(args, tg, quad, lane, er, tr);

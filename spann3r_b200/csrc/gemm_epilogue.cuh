@@ -64,11 +64,12 @@ __device__ __forceinline__ void epi_stage_cols(const GemmArgs& args, float* sb, 
 
 // Tile geometry: accumulator row r (0..127) of pixel tile (nb, th, tw) -> pixel (h, w); bw is a power of two.
 struct TileGeom {
-  int g, nb, h0, w0, lbw, bwm;
+  int g, ga, nb, h0, w0, lbw, bwm;   // ga: group whose rows this tile reads as A (a_swap)
 };
-__device__ __forceinline__ TileGeom make_geom(const GemmArgs& args, int g, int nb, int th, int tw) {
+__device__ __forceinline__ TileGeom make_geom(const GemmArgs& args, int g, int nb, int th, int tw, int col_first) {
   TileGeom t;
   t.g = g; t.nb = nb; t.h0 = th * args.bh; t.w0 = tw * args.bw;
+  t.ga = (args.a_swap && col_first >= args.swap_col0) ? (args.groups - 1 - g) : g;
   t.lbw = 31 - __clz(args.bw);
   t.bwm = args.bw - 1;
   return t;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void epi_tile_pre(const GemmArgs& args, const TileGeo
   er.valid = row_pixel(args, tg, r, er.h, er.w, er.pix);
   er.grow = (long long)tg.g * args.out_group_rows + er.pix;
   if (args.ln_stats != nullptr) {
-    const int ga = args.a_swap ? (args.groups - 1 - tg.g) : tg.g;
+    const int ga = tg.ga;
     const int np2 = args.ln_np >> 1;
     const int sub = lane & 15, half = lane >> 4;
     float s1 = 0.f, s2 = 0.f;
@@ -243,11 +244,12 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
     // croco/models/blocks.py:97-104 (self) / :154-160 (cross) + RoPE2D (pos_embed.py:112-159,
     // curope/kernels.cu:18-81): head dim 64 = [y half | x half], each half = 16 (u, v) pairs
     // (j, j+16) rotated by pos * 100^(-j/16).
-    role = args.q_role_base + col0 / args.q_C;  // 0 q, 1 k, 2 v
+    role = args.q_role_base + col0 / args.q_C;  // 0 q, 1 k, 2 v, 3 second k, 4 second v
     const int cc = col0 % args.q_C;
     head = cc >> 6;
     d0 = cc & 63;  // 0 or 32
-    if (role <= 1 && args.q_rope) {
+    const bool is_v = (role == 2 || role == 4);
+    if (!is_v && args.q_rope) {
       const int p = (d0 >> 5) ? er.px : er.py;
       const float2* cs = args.q_cs + p * 16;
 #pragma unroll
@@ -264,13 +266,13 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = to_tf32(v[j]);
-    if (role == 2) {   // V^T: for a fixed column the warp's 32 rows are 32 consecutive tokens -> already coalesced
+    if (is_v) {   // V^T: for a fixed column the warp's 32 rows are 32 consecutive tokens -> already coalesced
       if (er.valid) {
         const int heads = args.q_C >> 6;
         const int bidx = (int)(er.pix / args.q_ntok);
         const int t = (int)(er.pix - (long long)bidx * args.q_ntok);
         const long long gb = (long long)tg.g * args.q_nb + bidx;
-        float* op = args.vt_out + ((gb * heads + head) * 64 + d0) * (long long)args.q_ntok_pad + t;
+        float* op = (role == 2 ? args.vt_out : args.vt2_out) + ((gb * heads + head) * 64 + d0) * (long long)args.q_ntok_pad + t;
 #pragma unroll
         for (int j = 0; j < 32; ++j) op[(long long)j * args.q_ntok_pad] = v[j];
       }
@@ -311,7 +313,8 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
       float4 x = *reinterpret_cast<const float4*>(stg + (it * S::RPI + lr) * S::LD + cq);
       if constexpr (EPI == EPI_QKV) {
         if (key >= 0) {
-          float* op = (role == 0 ? args.q_out : args.k_out) + key + (long long)head * args.q_ntok * 64 + d0 + p * SW + cq;
+          float* op = (role == 0 ? args.q_out : role == 1 ? args.k_out : args.k2_out) + key +
+                      (long long)head * args.q_ntok * 64 + d0 + p * SW + cq;
           *reinterpret_cast<float4*>(op) = x;
         }
       } else {

@@ -36,7 +36,7 @@ class BlockW(C.Structure):
 
 
 class DecBlockW(C.Structure):
-    _fields_ = [("norm1", LN), ("qkv", Lin), ("proj", Lin), ("norm_y", LN), ("norm2", LN), ("q", Lin), ("kv", Lin),
+    _fields_ = [("norm1", LN), ("qkv", Lin), ("proj", Lin), ("norm_y", LN), ("norm2", LN), ("q", Lin),
                 ("cproj", Lin), ("norm3", LN), ("fc1", Lin), ("fc2", Lin)]
 
 
@@ -196,13 +196,14 @@ class PackedWeights:
         ps = [f"dust3r.dec_blocks.{l}", f"dust3r.dec_blocks2.{l}"]
         d = DecBlockW()
         d.norm1 = self._ln([p + ".norm1" for p in ps])
-        d.qkv = self._linear_ln([p + ".attn.qkv" for p in ps], [p + ".norm1" for p in ps])
+        # one launch per layer for the self-attention qkv AND the cross-attention k, v projections (the latter read the
+        # other stream's layer input, norm_y folded): per group [attn.qkv; cross_attn.projk; cross_attn.projv]
+        d.qkv = self._linear_ln([p + s for p in ps for s in (".attn.qkv", ".cross_attn.projk", ".cross_attn.projv")],
+                                [p + s for p in ps for s in (".norm1", ".norm_y", ".norm_y")])
         d.proj = self._linear([p + ".attn.proj" for p in ps])
         d.norm_y = self._ln([p + ".norm_y" for p in ps])
         d.norm2 = self._ln([p + ".norm2" for p in ps])
         d.q = self._linear_ln([p + ".cross_attn.projq" for p in ps], [p + ".norm2" for p in ps])
-        # per group: [projk; projv], both applied to norm_y(y) (croco/models/blocks.py:188-189)
-        d.kv = self._linear_ln([p + f".cross_attn.proj{r}" for p in ps for r in "kv"], [p + ".norm_y" for p in ps for _ in "kv"])
         d.cproj = self._linear([p + ".cross_attn.proj" for p in ps])
         d.norm3 = self._ln([p + ".norm3" for p in ps])
         d.fc1 = self._linear_ln([p + ".mlp.fc1" for p in ps], [p + ".norm3" for p in ps])

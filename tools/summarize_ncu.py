@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Summarise an `ncu --csv` launch list (metrics gpu__time_duration.sum [+ dram__bytes_read/write.sum]) into a
+per-kernel markdown table, and (with --traffic OUT.json) the DRAM bytes per GEMM launch that bench.py reports as
+roofline.traffic.  Usage: python tools/summarize_ncu.py launches.csv [--traffic profiles/gemm_traffic.json] [--title T]"""
+import csv
+import json
+import re
+import sys
+from collections import defaultdict
+
+path = sys.argv[1]
+title = sys.argv[sys.argv.index("--title") + 1] if "--title" in sys.argv else path
+rows = []
+with open(path, newline="") as f:
+    lines = [l for l in f if l.startswith('"')]
+for r in csv.DictReader(lines):
+    rows.append(r)
+per_launch = defaultdict(dict)
+for r in rows:
+    per_launch[int(r["ID"])]["name"] = r["Kernel Name"]
+    per_launch[int(r["ID"])]["grid"] = r["Grid Size"]
+    v = float(r["Metric Value"].replace(",", ""))
+    unit = r["Metric Unit"]
+    if r["Metric Name"] == "gpu__time_duration.sum":
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
+    else:
+        v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+    per_launch[int(r["ID"])][r["Metric Name"]] = v
+
+
+def short(n):
+    n = re.sub(r"^void ", "", n)
+    n = re.sub(r"\(.*\)$", "", n)
+    return n[:90]
+
+
+agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+for i, d in per_launch.items():
+    a = agg[short(d["name"])]
+    a[0] += 1
+    a[1] += d.get("gpu__time_duration.sum", 0.0)
+    a[2] += d.get("dram__bytes_read.sum", 0.0)
+    a[3] += d.get("dram__bytes_write.sum", 0.0)
+tot = sum(a[1] for a in agg.values())
+print(f"# {title}\n")
+print(f"{len(per_launch)} launches, sum of (serialised, cold-cache) durations {tot / 1e3:.2f} ms\n")
+print("| kernel | launches | total ms | share | avg us | DRAM read MB/launch | DRAM write MB/launch |")
+print("|---|---:|---:|---:|---:|---:|---:|")
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"| `{k}` | {a[0]} | {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0]:.1f} | {a[2] / a[0] / 1e6:.2f} | {a[3] / a[0] / 1e6:.2f} |")
+if "--traffic" in sys.argv:
+    out = sys.argv[sys.argv.index("--traffic") + 1]
+    g = [d for d in per_launch.values() if "gemm" in d["name"] and "bf16x3" in d["name"]]
+    rd = sum(d.get("dram__bytes_read.sum", 0.0) for d in g)
+    wr = sum(d.get("dram__bytes_write.sum", 0.0) for d in g)
+    json.dump({"kernel": "gemm_bf16x3_kernel<*> + gemm2_bf16x3_kernel<*> (all launches of one 10-frame 512x384 sequence)",
+               "launches": len(g), "dram_bytes_per_launch": (rd + wr) / max(len(g), 1), "dram_read_bytes_total": rd,
+               "dram_write_bytes_total": wr,
+               "algorithmic_bytes_note": "weights 2.63 GB per frame-step are the compulsory HBM traffic: 25 GB / sequence",
+               "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum ({path})"},
+              open(out, "w"), indent=1)
