@@ -128,6 +128,7 @@ class SpatialMemory:
         self.sim_thresh = sim_thresh
         self.num_patches = num_patches
         self.bank = None
+        self._sim_host = None
         self.init_mem()
 
     def init_mem(self):
@@ -165,19 +166,40 @@ class SpatialMemory:
         self.engine.memory_append(self.bank, feat_k, feat_v)
 
     def check_sim(self, feat_k, thresh=0.7):  # :97-118
+        return self.check_sim_finish(self.check_sim_async(feat_k, thresh), thresh)
+
+    def check_sim_async(self, feat_k, thresh=0.7):
+        """First half of check_sim: enqueue the similarity kernels and an async copy of max(mean_corr) to pinned host
+        memory.  The reference reads the value with a blocking `.item()` right away (:114); the forward loop instead
+        enqueues this as soon as feat_k exists and reads it (check_sim_finish) after the DPT heads and the value encoder
+        have been enqueued, so the GPU never drains while the host decides whether to append.  Same inputs (the bank does
+        not change in between), same value, same decision."""
         if self.bank is None or self.bank.len == 0 or thresh == 1.0:
-            return False
+            return None
         mean_corr = self.engine.check_sim(self.bank, feat_k, self.wm)
-        mx = float(mean_corr.max())            # host sync, as in the reference (:114)
+        if self._sim_host is None:
+            self._sim_host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+        self._sim_host.copy_(mean_corr.max().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def check_sim_finish(self, pending, thresh=0.7):
+        if pending is None:
+            return False
+        pending.synchronize()
+        mx = float(self._sim_host[0])
         if mx > thresh:
             print("Similarity detected:", mx)
             return True
         return False
 
-    def add_mem_check(self, feat_k, feat_v, pts_cur=None, img_cur=None):  # :120-143
+    def add_mem_check(self, feat_k, feat_v, pts_cur=None, img_cur=None, sim_pending="now"):  # :120-143
         if self.num_patches is None:
             self.num_patches = feat_k.shape[1]
-        if self.check_sim(feat_k, thresh=self.sim_thresh):
+        if sim_pending == "now":
+            sim_pending = self.check_sim_async(feat_k, thresh=self.sim_thresh)
+        if self.check_sim_finish(sim_pending, thresh=self.sim_thresh):
             return
         self.add_mem(feat_k, feat_v, pts_cur, img_cur)
         self.wm += 1
@@ -322,11 +344,12 @@ class Spann3R(ParamModule):
             feat_fuse = sp_mem.memory_read(feat_k2, res=True) if feat_k2 is not None else feat1
             eng.decode(feat_fuse, feat2)
             feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
+            sim = sp_mem.check_sim_async(feat_k1, thresh=sp_mem.sim_thresh)   # read back in add_mem_check below
             pts, conf = eng.heads()
             res1 = {"pts3d": pts[0], "conf": conf[0]}
             res2 = {"pts3d": pts[1], "conf": conf[1]}
             mem_v = eng.value(res1["pts3d"], feat_k1)            # encode_cur_value(...) + feat_k1
-            sp_mem.add_mem_check(feat_k1, mem_v)
+            sp_mem.add_mem_check(feat_k1, mem_v, sim_pending=sim)
             res2["pts3d_in_other_view"] = res2.pop("pts3d")
             if preds is None:
                 preds = [res1]
