@@ -131,6 +131,20 @@ int s3r_attention(const float* q, const float* k, const float* vt, int bh, int h
  * scratch256 = 256 floats of device scratch.  Deterministic. */
 int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, void* stream);
 
+/* ---- input adapter: the reference's CPU preprocessing in front of the path -----------
+ * spann3r/datasets/demo.py:57-86 -> dust3r/datasets/base/base_stereo_view_dataset.py:143-194 (centre crop, Lanczos
+ * down-scale, centred crop) -> dust3r/utils/image.py:23 (ToTensor + Normalize).  The down-scale is Pillow's 8-bit
+ * separable resampler (Resample.c), reproduced bit-exactly; the host supplies Pillow's coefficient tables:
+ * bounds [n, 2] int32 (first source index, tap count) and kk [n, ksize] int32 (22-bit fixed point), already shifted so
+ * that index 0 is the first row / column passed in.
+ * s3r_resample_h_u8: src = RGB uint8 rows (row_stride bytes apart), `rows` rows -> dst [rows, out_cols, 3] uint8;
+ *   max_span = largest number of source pixels any block of 128 consecutive output columns touches.
+ * s3r_resample_v_u8_norm: tmp [*, cols, 3] uint8 -> dst [3, out_rows, cols] fp32 = ((v / 255) - 0.5) / 0.5. */
+int s3r_resample_h_u8(const uint8_t* src, int64_t row_stride, int rows, int out_cols, const int32_t* bounds,
+                      const int32_t* kk, int ksize, int max_span, uint8_t* dst, void* stream);
+int s3r_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int32_t* bounds, const int32_t* kk, int ksize,
+                           float* dst, void* stream);
+
 /* ---- model level: the per-frame forward path -------------------------------------------------
  * Packed weights.  The host (spann3r_b200/weights.py) converts the reference state dict ONCE into
  * split-bf16 planes laid out [groups*N, taps*Kc] (K contiguous) plus fp32 biases / LayerNorm params,

@@ -145,6 +145,15 @@ int s3r_gemm_tile_n(const s3r_gemm_desc* d) {
   return plan.bn;
 }
 
+int s3r_resample_h_u8(const uint8_t* src, int64_t row_stride, int rows, int out_cols, const int32_t* bounds,
+                      const int32_t* kk, int ksize, int max_span, uint8_t* dst, void* stream) {
+  return launch_resample_h_u8(src, row_stride, rows, out_cols, bounds, kk, ksize, max_span, dst, S(stream));
+}
+int s3r_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int32_t* bounds, const int32_t* kk, int ksize,
+                           float* dst, void* stream) {
+  return launch_resample_v_u8_norm(tmp, cols, out_rows, bounds, kk, ksize, dst, S(stream));
+}
+
 int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, void* stream) {
   return launch_conf_score(conf, n, scratch256, out, S(stream));
 }

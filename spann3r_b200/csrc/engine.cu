@@ -644,7 +644,8 @@ int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
   // until refinenet4.  They are small (2 .. 96 pixel tiles) and latency-bound, so levels 2-4 run on side streams
   // beside level 1 (forked / joined with events; single stream while per-launch profiling is on).  The launch ORDER
   // in the plan cache is the same either way.
-  const bool par = !e->profiling;
+  static const bool par_env = getenv("S3R_HEADS_PAR") ? atoi(getenv("S3R_HEADS_PAR")) != 0 : true;   // A/B switch
+  const bool par = par_env && !e->profiling;
   if (par) {
     cudaEventRecord(e->ev_fork, st);
     for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(e->side[i], e->ev_fork, 0);

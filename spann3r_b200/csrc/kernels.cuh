@@ -55,6 +55,12 @@ int launch_split_transpose(const float* x, int B, int T, int C, __nv_bfloat16* o
 int launch_check_sim(const float* feat, const float* wm, long long wm_batch_stride, int B, int T, int P, int C,
                      float* scratch, float* out, cudaStream_t st);
 
+// input adapter (preprocess.cu): Pillow's 8-bit Lanczos resample passes, crops folded in
+int launch_resample_h_u8(const uint8_t* src, long long row_stride, int rows, int out_cols, const int* bounds,
+                         const int* kk, int ksize, int max_span, uint8_t* dst, cudaStream_t st);
+int launch_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int* bounds, const int* kk, int ksize,
+                              float* dst, cudaStream_t st);
+
 int launch_conf_score(const float* conf, long long n, float* scratch256, float* out, cudaStream_t st);
 
 // fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output
