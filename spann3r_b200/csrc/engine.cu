@@ -62,20 +62,7 @@ struct PlanCache {
   size_t gc = 0, ac = 0;
   bool building = true;
   void begin() { gc = ac = 0; }
-  void end() {
-    if (building) {
-      // chain: every GEMM prefetches the weight planes of the next GEMM of the stage into L2 (<= 32 MB each)
-      static const bool on = (getenv("S3R_PREFETCH") != nullptr);   // measured: no gain on B200 (-1%), off by default
-      for (size_t i = 0; on && i + 1 < gemms.size(); ++i) {
-        const GemmPlan& nx = gemms[i + 1];
-        if (nx.b_bytes == 0 || nx.b_bytes > (32ull << 20)) continue;
-        gemms[i].args.pf_base0 = (const unsigned char*)nx.b_hi;
-        gemms[i].args.pf_base1 = (const unsigned char*)nx.b_lo;
-        gemms[i].args.pf_bytes = nx.b_bytes;
-      }
-    }
-    building = false;
-  }
+  void end() { building = false; }
 };
 
 }  // namespace
@@ -644,8 +631,7 @@ int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
   // until refinenet4.  They are small (2 .. 96 pixel tiles) and latency-bound, so levels 2-4 run on side streams
   // beside level 1 (forked / joined with events; single stream while per-launch profiling is on).  The launch ORDER
   // in the plan cache is the same either way.
-  static const bool par_env = getenv("S3R_HEADS_PAR") ? atoi(getenv("S3R_HEADS_PAR")) != 0 : true;   // A/B switch
-  const bool par = par_env && !e->profiling;
+  const bool par = !e->profiling;
   if (par) {
     cudaEventRecord(e->ev_fork, st);
     for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(e->side[i], e->ev_fork, 0);

@@ -205,14 +205,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9): TMEM lane quadrant
     // warp & 3, column half (warp - 2) >> 2
-    if (args.pf_bytes) {   // pull the next GEMM's weights into L2 while this kernel's main loop runs
-      const unsigned long long lines = args.pf_bytes >> 7;
-      for (unsigned long long ln = (unsigned long long)blockIdx.x * (32 * kEpiWarps) + (threadIdx.x - 64); ln < lines;
-           ln += (unsigned long long)gridDim.x * (32 * kEpiWarps)) {
-        prefetch_l2(args.pf_base0 + (ln << 7));
-        prefetch_l2(args.pf_base1 + (ln << 7));
-      }
-    }
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;
     constexpr int CH = BN / 64;  // 32-column chunks per warp
@@ -417,14 +409,8 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   if (N <= 64) { bn = 64; two = 0; }
   // many-wave GEMMs whose width is a multiple of 256 (the batched encoder): 256 x 256 pair tiles halve the number of
   // per-tile epilogue preambles (LayerNorm statistics, staged columns) -- measured in situ, not visible in the sweep
-  static const int p2256 = getenv("S3R_P2256") ? atoi(getenv("S3R_P2256")) : 1;
-  static const int small2 = getenv("S3R_SMALL2") ? atoi(getenv("S3R_SMALL2")) : 1;
   const long long tiles128 = m_tiles * nt128;
-  if (p2256 && two && taps == 1 && N % 256 == 0 && tiles128 >= 400) bn = 256;
-  if (!small2 && two && tiles128 < 400 && taps == 1) {   // experiment: 1-CTA tiles for the single-wave linears
-    two = 0;
-    bn = (c128 < c64) ? 128 : 64;
-  }
+  if (two && taps == 1 && N % 256 == 0 && tiles128 >= 400) bn = 256;
   if (force_bn == 0 && legal2 && (g2_mode == 128 || g2_mode == 256)) {
     two = 1;
     bn = (g2_mode == 256 && N % 256 == 0) ? 256 : 128;
@@ -468,8 +454,6 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
     plan->grid = dim3((unsigned)((total < num_sms()) ? total : num_sms()), 1, 1);  // persistent: <= 1 CTA per SM
   }
   plan->flops = 2.0 * (double)NB * H * W * groups * (double)N * (double)Kc * taps;
-  plan->b_hi = b_hi; plan->b_lo = b_lo;
-  plan->b_bytes = (unsigned long long)(b_group_rows * (groups - 1) + N) * (unsigned long long)ldb * 2ull;
   return 0;
 }
 

@@ -59,9 +59,6 @@ struct GemmArgs {
   float* q_out; float* k_out; float* vt_out;
   float* k2_out; float* vt2_out;       // roles 3 / 4: a second K / V^T pair (the cross-attention K/V of the merged decoder launch)
   float q_scale;
-  // L2 prefetch of the NEXT GEMM's weight planes (static data): issued by the idle epilogue warps at kernel start so
-  // that the next kernel's first touch of its weights hits L2 instead of HBM (small-M GEMMs are latency bound)
-  const unsigned char* pf_base0; const unsigned char* pf_base1; unsigned long long pf_bytes;
   // EPI_HEADTAIL
   const float* ht_w;       // [G, 4, 128]
   const float* ht_b;       // [G, 4]
@@ -75,7 +72,6 @@ struct GemmPlan {
   int bn;          // 64 / 128 / 256
   int two_cta;     // 1: 256 x bn tiles on CTA pairs (gemm2.cu)
   double flops;    // algorithmic 2*M*N*K (all groups), for roofline accounting
-  const void* b_hi; const void* b_lo; unsigned long long b_bytes;   // this plan's weight planes (for the predecessor's prefetch)
 };
 
 // Encodes the four tensor maps and picks the tile shape.  Returns 0 or a negative error.

@@ -263,14 +263,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9), own 128 rows
-    if (args.pf_bytes) {   // pull the next GEMM's weights into L2 while this kernel's main loop runs
-      const unsigned long long lines = args.pf_bytes >> 7;
-      for (unsigned long long ln = (unsigned long long)blockIdx.x * 256 + (threadIdx.x - 64); ln < lines;
-           ln += (unsigned long long)gridDim.x * 256) {
-        prefetch_l2(args.pf_base0 + (ln << 7));
-        prefetch_l2(args.pf_base1 + (ln << 7));
-      }
-    }
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;            // column half handled by this warp
     int it = 0;

@@ -344,8 +344,7 @@ class Spann3R(ParamModule):
             feat_fuse = sp_mem.memory_read(feat_k2, res=True) if feat_k2 is not None else feat1
             eng.decode(feat_fuse, feat2)
             feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
-            # similarity gate: enqueue now, read back in add_mem_check below (S3R_SIM_NOW=1: blocking read here, A/B switch)
-            sim = "now" if os.environ.get("S3R_SIM_NOW") == "1" else sp_mem.check_sim_async(feat_k1, thresh=sp_mem.sim_thresh)
+            sim = sp_mem.check_sim_async(feat_k1, thresh=sp_mem.sim_thresh)   # read back in add_mem_check below
             pts, conf = eng.heads()
             res1 = {"pts3d": pts[0], "conf": conf[0]}
             res2 = {"pts3d": pts[1], "conf": conf[1]}
