@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Print per-stage relative errors of the CUDA engine vs the oracle (GPU, strict fp32). Debug aid."""
+"""Print per-stage relative errors of the CUDA engine vs the oracle (GPU, strict fp32). Debug aid (parity checker: lives under tests/ because it imports the oracle)."""
 import os
 import sys
 import time
