@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace s3r {
@@ -25,8 +26,15 @@ constexpr int D = 64;
 constexpr int Q_BYTES = BQ * D * 4;       // 32 KB (2 swizzle atoms of [128 x 32 f32])
 constexpr int K_BYTES = BKV * D * 4;      // 32 KB
 constexpr int V_BYTES = D * BKV * 4;      // 32 KB (4 atoms of [64 x 32 f32])
-constexpr int KV_STAGES = 3;
-constexpr int SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 1024 + 256;
+// PAIR = false: one 128-query tile per CTA, the two softmax groups take alternate KV blocks (merged at the end);
+// PAIR = true: two query tiles per CTA, group g owns tile g for ALL KV blocks -- K/V are loaded once per 256 queries
+// and there is no merge (many-wave launches: the batched encoder).
+template <bool PAIR>
+struct Cfg {
+  static constexpr int QB = PAIR ? 2 * Q_BYTES : Q_BYTES;
+  static constexpr int KV_STAGES = PAIR ? 2 : 3;
+  static constexpr int SMEM = QB + KV_STAGES * (K_BYTES + V_BYTES) + 1024 + 256;
+};
 constexpr uint32_t TMEM_COLS = 512;       // group g: S/P at [g*192, +128), O at [g*192+128, +64)
 constexpr int kThreads = 384;             // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1, 2: softmax
 }  // namespace attn
@@ -63,14 +71,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // while one group runs its softmax the tensor core serves the other group's QK^T / PV, and the two partial results
 // are merged once at the end (flash-decoding style).  P never touches shared memory: the softmax threads overwrite
 // their S row in TMEM with tf32 probabilities (tcgen05.st) and the PV MMA takes its A operand from TMEM.
+template <bool PAIR>
 __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __grid_constant__ AttnArgs args) {
   using namespace attn;
+  constexpr int KV_STAGES = Cfg<PAIR>::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would lose the address
   // space and turn every access through `smem` into a generic LD / ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + Q_BYTES;                            // stage s: K at s*(K+V), V after K
+  uint8_t* sKV = sQ + Cfg<PAIR>::QB;                      // stage s: K at s*(K+V), V after K
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KV_STAGES * (K_BYTES + V_BYTES));
   uint64_t* q_full = bars;            // 1
   uint64_t* kv_full = bars + 1;       // 3
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
+  const int q0 = (PAIR ? 2 : 1) * blockIdx.x * BQ;       // PAIR: group g's tile starts at q0 + g * BQ
   const int bh = blockIdx.y;
   const int nblk = (args.nk + BKV - 1) / BKV;
 
@@ -114,9 +124,12 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_3d(sQ, &args.tmQ, q_full, 0, q0, bh);
-      tma_load_3d(sQ + Q_BYTES / 2, &args.tmQ, q_full, 32, q0, bh);
+      mbar_arrive_expect_tx(q_full, Cfg<PAIR>::QB);
+#pragma unroll
+      for (int t = 0; t < (PAIR ? 2 : 1); ++t) {
+        tma_load_3d(sQ + t * Q_BYTES, &args.tmQ, q_full, 0, q0 + t * BQ, bh);
+        tma_load_3d(sQ + t * Q_BYTES + Q_BYTES / 2, &args.tmQ, q_full, 32, q0 + t * BQ, bh);
+      }
       for (int j = 0; j < nblk; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
@@ -140,31 +153,30 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t aQ = __shfl_sync(0xffffffffu, smem_u32(sQ), 0);
       const uint32_t aKV = __shfl_sync(0xffffffffu, smem_u32(sKV), 0);
-      auto issue_s = [&](int j) {   // S_g = Q K_j^T, g = j & 1
+      // S_g = Q_g K_j^T into group g's S/P columns.  !PAIR: one query tile, g = j & 1.  PAIR: group g's own tile.
+      auto issue_s = [&](int g, int j) {
         const int st = j % KV_STAGES;
         mbar_wait(&kv_full[st], (j / KV_STAGES) & 1);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t aK = aKV + st * (K_BYTES + V_BYTES);
-          const uint32_t tmem_s = tmem_u + (j & 1) * 192;
+          const uint32_t aQg = aQ + (PAIR ? g * Q_BYTES : 0);
+          const uint32_t tmem_s = tmem_u + g * 192;
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            const uint64_t dq = umma_desc_sw128_kmajor(aQ + a * (Q_BYTES / 2));
+            const uint64_t dq = umma_desc_sw128_kmajor(aQg + a * (Q_BYTES / 2));
             const uint64_t dk = umma_desc_sw128_kmajor(aK + a * (K_BYTES / 2));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, (a | kk) != 0);
           }
-          umma_commit(&s_full[j & 1]);
+          umma_commit(&s_full[g]);
         }
         __syncwarp();
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      if (nblk > 1) issue_s(1);
-      for (int j = 0; j < nblk; ++j) {
-        const int g = j & 1;
+      // O_g (+)= P_g V_j (P from TMEM); `first` = group g's first block; `release` frees the KV stage afterwards
+      auto issue_pv = [&](int g, int j, bool first, bool release, uint32_t p_parity) {
         const int st = j % KV_STAGES;
-        mbar_wait(&p_full[g], (j >> 1) & 1);
+        mbar_wait(&p_full[g], p_parity);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t aV = aKV + st * (K_BYTES + V_BYTES) + K_BYTES;
@@ -174,13 +186,30 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
             const uint64_t dv = umma_desc_sw128_kmajor(aV + a * (V_BYTES / 4));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_tf32_ts(tmem_o, tmem_p + a * 32 + kk * 8, dv + 2 * kk, idesc_o, (j >= 2) || (a | kk) != 0);
+              umma_tf32_ts(tmem_o, tmem_p + a * 32 + kk * 8, dv + 2 * kk, idesc_o, !first || (a | kk) != 0);
           }
           umma_commit(&o_full[g]);
-          umma_commit(&kv_empty[st]);
+          if (release) umma_commit(&kv_empty[st]);
         }
         __syncwarp();
-        if (j + 2 < nblk) issue_s(j + 2);   // same group's next block: its S/P columns are free once PV_j retires
+      };
+      mbar_wait(q_full, 0);
+      if constexpr (!PAIR) {
+        issue_s(0, 0);
+        if (nblk > 1) issue_s(1, 1);
+        for (int j = 0; j < nblk; ++j) {
+          issue_pv(j & 1, j, j < 2, true, (j >> 1) & 1);
+          if (j + 2 < nblk) issue_s(j & 1, j + 2);   // same group's next block: its S/P columns are free once PV_j retires
+        }
+      } else {
+        issue_s(0, 0);
+        issue_s(1, 0);
+        for (int j = 0; j < nblk; ++j) {
+          issue_pv(0, j, j == 0, false, j & 1);
+          if (j + 1 < nblk) issue_s(0, j + 1);       // needs K_{j+1} (2-stage ring) and group 0's S/P columns (in-order pipe)
+          issue_pv(1, j, j == 0, true, j & 1);        // both groups' P.V of block j issued -> the stage can be refilled
+          if (j + 1 < nblk) issue_s(1, j + 1);
+        }
       }
     }
   }
@@ -199,7 +228,7 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
     constexpr float kLog2e = 1.4426950408889634f;
     float ref = -INFINITY, l = 0.f;
     int it = 0;
-    for (int j = g; j < nblk; j += 2, ++it) {
+    for (int j = PAIR ? 0 : g; j < nblk; j += (PAIR ? 1 : 2), ++it) {   // PAIR: every block, for this group's own tile
       mbar_wait(&s_full[g], it & 1);
       tc_fence_after_sync();
       const int kbase = j * BKV;
@@ -280,28 +309,43 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
 #pragma unroll
       for (int i = 0; i < D; ++i) o[i] = 0.f;
     }
-    // ---- merge the two groups' partial results through shared memory (the KV ring is drained by now) ----
-    float* mg = reinterpret_cast<float*>(sKV);        // [66][128]: o[0..63], m, l  (column = query row)
     named_bar_sync(1, 256);   // both groups have seen their last o_full: every MMA that reads the KV ring has retired
-    if (g == 1) {
+    bool writer = true;
+    int qt0 = q0;                                      // first query row of the tile this thread's group writes
+    constexpr int LD = D + 4;
+    float* stg;
+    if constexpr (!PAIR) {
+      // ---- merge the two groups' partial results through shared memory (the KV ring is drained by now) ----
+      float* mg = reinterpret_cast<float*>(sKV);        // [66][128]: o[0..63], m, l  (column = query row)
+      if (g == 1) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) mg[i * 128 + r] = o[i];
-      mg[64 * 128 + r] = m;
-      mg[65 * 128 + r] = l;
+        for (int i = 0; i < D; ++i) mg[i * 128 + r] = o[i];
+        mg[64 * 128 + r] = m;
+        mg[65 * 128 + r] = l;
+      }
+      named_bar_sync(1, 256);
+      writer = (g == 0);
+      if (writer) {
+        const float m1 = mg[64 * 128 + r], l1 = mg[65 * 128 + r];
+        const float mm = fmaxf(m, m1);
+        const float w0 = __expf(m - mm), w1 = (l1 > 0.f) ? __expf(m1 - mm) : 0.f;
+        const float inv = 1.0f / (l * w0 + l1 * w1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] = (o[i] * w0 + mg[i * 128 + r] * w1) * inv;
+      }
+      stg = reinterpret_cast<float*>(sKV + 40 * 1024) + quad * 32 * LD;   // behind the merge buffer
+    } else {
+      // each group owns a complete softmax over all keys for its tile: normalise and write
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int i = 0; i < D; ++i) o[i] *= inv;
+      qt0 = q0 + g * BQ;
+      stg = reinterpret_cast<float*>(sKV) + (g * 4 + quad) * 32 * LD;
     }
-    named_bar_sync(1, 256);
-    if (g == 0) {
-      const float m1 = mg[64 * 128 + r], l1 = mg[65 * 128 + r];
-      const float mm = fmaxf(m, m1);
-      const float w0 = __expf(m - mm), w1 = (l1 > 0.f) ? __expf(m1 - mm) : 0.f;
-      const float inv = 1.0f / (l * w0 + l1 * w1);
-#pragma unroll
-      for (int i = 0; i < D; ++i) o[i] = (o[i] * w0 + mg[i * 128 + r] * w1) * inv;
+    if (writer) {
       // Transposed store (see gemm_epilogue.cuh): thread = row would touch 32 different cache lines per 16-byte
-      // access; stage the warp's 32 x 64 tile in the drained KV ring (behind the merge buffer) and write it so that
-      // 16 consecutive lanes cover one row's 256 bytes.
-      constexpr int LD = D + 4;
-      float* stg = reinterpret_cast<float*>(sKV + 40 * 1024) + quad * 32 * LD;
+      // access; stage the warp's 32 x 64 tile in the drained KV ring and write it so that 16 consecutive lanes cover
+      // one row's 256 bytes.
       {
         float4* sp = reinterpret_cast<float4*>(stg + lane * LD);
 #pragma unroll
@@ -311,9 +355,9 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
       const int b = bh / args.heads, h = bh - b * args.heads;
       const int cq = (lane & 15) * 4;
 #pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
-        const int rr = it * 2 + (lane >> 4);
-        const int q = q0 + quad * 32 + rr;
+      for (int it2 = 0; it2 < 16; ++it2) {
+        const int rr = it2 * 2 + (lane >> 4);
+        const int q = qt0 + quad * 32 + rr;
         if (q < args.nq) {
           const float4 x = *reinterpret_cast<const float4*>(stg + rr * LD + cq);
           const long long off = ((long long)b * args.nq + q) * args.ldo + h * D + cq;
@@ -369,31 +413,40 @@ int attn_plan_init(AttnPlan* plan, const float* q, const float* k, const float* 
     if (r) return r;
   }
   a.nq = nq; a.nk = nk; a.heads = heads;
-  plan->grid = dim3((nq + BQ - 1) / BQ, BH);
+  // many-wave launches (the batched encoder: 960 CTAs on 148 SMs) take two query tiles per CTA
+  const int q_tiles = (nq + BQ - 1) / BQ;
+  static const int pair_on = getenv("S3R_ATTN_PAIR") ? atoi(getenv("S3R_ATTN_PAIR")) : 1;   // 0: A/B switch
+  plan->pair = (pair_on && q_tiles % 2 == 0 && (long long)q_tiles * BH >= 3 * 148) ? 1 : 0;
+  plan->grid = dim3(plan->pair ? q_tiles / 2 : q_tiles, BH);
   plan->flops = 4.0 * BH * (double)nq * nk * 64;
   return 0;
 }
 
-int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo,
-                cudaStream_t st) {
+template <bool PAIR>
+static int attn_launch_t(const AttnPlan& plan, const AttnArgs& a, cudaStream_t st) {
   using namespace attn;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM);
     if (e != cudaSuccess) {
-      set_error("attention: cudaFuncSetAttribute(smem=%d): %s", SMEM, cudaGetErrorString(e));
+      set_error("attention: cudaFuncSetAttribute(smem=%d): %s", Cfg<PAIR>::SMEM, cudaGetErrorString(e));
       return -5;
     }
     attr_set = true;
   }
-  AttnArgs a = plan.args;
-  a.o_hi = o_hi; a.o_lo = o_lo; a.o_f32 = o_f32; a.ldo = ldo;
-  cudaError_t e = launch_pdl(attention_kernel, plan.grid, dim3(kThreads), SMEM, st, a);
+  cudaError_t e = launch_pdl(attention_kernel<PAIR>, plan.grid, dim3(kThreads), Cfg<PAIR>::SMEM, st, a);
   if (e != cudaSuccess) {
     set_error("attention launch failed: %s", cudaGetErrorString(e));
     return -6;
   }
   return 0;
+}
+
+int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, float* o_f32, long long ldo,
+                cudaStream_t st) {
+  AttnArgs a = plan.args;
+  a.o_hi = o_hi; a.o_lo = o_lo; a.o_f32 = o_f32; a.ldo = ldo;
+  return plan.pair ? attn_launch_t<true>(plan, a, st) : attn_launch_t<false>(plan, a, st);
 }
 
 int launch_attention(const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk, int nk_pad,

@@ -37,6 +37,7 @@ struct AttnArgs {
 struct AttnPlan {
   AttnArgs args;
   dim3 grid;
+  int pair;        // 1: two query tiles per CTA (attention.cu, PAIR)
   double flops;
 };
 int attn_plan_init(AttnPlan* plan, const float* q, const float* k, const float* vt, int BH, int heads, int nq, int nk,

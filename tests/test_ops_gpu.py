@@ -181,9 +181,14 @@ def test_qkv_rope_attention(L, B, gh, gw, heads, groups):
     assert rel_l2(oh.double() + ol.double(), ref) < TOL_ATTN
 
 
-def test_cross_attention_shapes(L):
+@pytest.mark.parametrize("BH,heads,nq,nk", [
+    (6, 3, 196, 300),
+    # many-wave launches take the query-tile-pair variant (two tiles per CTA, no merge): full / ragged key blocks,
+    # ragged last query tile, a single key block
+    (96, 16, 768, 768), (128, 16, 512, 300), (160, 16, 700, 768), (256, 16, 256, 100),
+])
+def test_cross_attention_shapes(L, BH, heads, nq, nk):
     """nq != nk and non-multiple-of-128 sizes through the attention core alone."""
-    BH, heads, nq, nk = 6, 3, 196, 300
     def tf32(x):  # the kernel's contract: operands already rounded to tf32 (done by the QKV epilogue)
         return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
     q = tf32(_rand(BH, nq, 64, seed=20, scale=0.3))
