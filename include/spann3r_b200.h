@@ -145,6 +145,13 @@ int s3r_resample_h_u8(const uint8_t* src, int64_t row_stride, int rows, int out_
 int s3r_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int32_t* bounds, const int32_t* kk, int ksize,
                            float* dst, void* stream);
 
+/* ---- post-path geometry (first step) ---------------------------------------------------
+ * dust3r/post_process.py:12-60 estimate_focal_knowing_depth(pts3d, pp, focal_mode='weiszfeld') as demo.py:148-150 calls
+ * it: pts3d [b, h, w, 3] fp32 (device), principal point (ppx, ppy), `iters` re-weighting rounds (the reference: 10),
+ * result clipped to [lo, hi] -> focal [b] (device).  scratch: b * 148 * 2 floats.  Deterministic. */
+int s3r_focal_weiszfeld(const float* pts3d, int b, int h, int w, float ppx, float ppy, int iters, float lo, float hi,
+                        float* scratch, float* focal, void* stream);
+
 /* ---- model level: the per-frame forward path -------------------------------------------------
  * Packed weights.  The host (spann3r_b200/weights.py) converts the reference state dict ONCE into
  * split-bf16 planes laid out [groups*N, taps*Kc] (K contiguous) plus fp32 biases / LayerNorm params,

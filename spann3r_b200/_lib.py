@@ -56,6 +56,7 @@ _PROTOS = {
     "s3r_gemm_tile_n": (_i, [C.POINTER(GemmDesc)]),
     "s3r_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "s3r_conf_score": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "s3r_focal_weiszfeld": (_i, [_vp, _i, _i, _i, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
     "s3r_resample_h_u8": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "s3r_resample_v_u8_norm": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
 }

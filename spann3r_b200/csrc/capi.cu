@@ -154,6 +154,11 @@ int s3r_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int
   return launch_resample_v_u8_norm(tmp, cols, out_rows, bounds, kk, ksize, dst, S(stream));
 }
 
+int s3r_focal_weiszfeld(const float* pts3d, int b, int h, int w, float ppx, float ppy, int iters, float lo, float hi,
+                        float* scratch, float* focal, void* stream) {
+  return launch_focal_weiszfeld(pts3d, b, h, w, ppx, ppy, iters, lo, hi, scratch, focal, S(stream));
+}
+
 int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, void* stream) {
   return launch_conf_score(conf, n, scratch256, out, S(stream));
 }

@@ -62,6 +62,10 @@ int launch_resample_h_u8(const uint8_t* src, long long row_stride, int rows, int
 int launch_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int* bounds, const int* kk, int ksize,
                               float* dst, cudaStream_t st);
 
+// post-path geometry (geometry.cu): scratch = B * 148 * 2 floats
+int launch_focal_weiszfeld(const float* pts3d, int B, int H, int W, float ppx, float ppy, int iters, float lo, float hi,
+                           float* scratch, float* focal, cudaStream_t st);
+
 int launch_conf_score(const float* conf, long long n, float* scratch256, float* out, cudaStream_t st);
 
 // fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output
