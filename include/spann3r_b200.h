@@ -220,8 +220,15 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
 int s3r_engine_keyheads(s3r_engine* e, const float* feat1, const float* feat2, float* k1, float* k2, void* stream);
 /* dust3r/model.py:207-211 + heads/dpt_head.py + postprocess.py: pts [2,B,H,W,3], conf [2,B,H,W] */
 int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream);
-/* spann3r/model.py:305-320 encode_cur_value, plus the `cur_v + feat_k1` of :519-521: out [B,N,1024] */
-int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, float* out, void* stream);
+/* spann3r/model.py:305-320 encode_cur_value, plus the `cur_v + feat_k1` of :519-521: out [B,N,1024].
+ * pts3d = head 1's pointmap exactly as s3r_engine_heads wrote it ([B,H,W,3]).  flags:
+ *   S3R_VALUE_PTS_TRANSPOSED  portrait frame (H > W): the reference's landscape wrapper (dust3r/utils/misc.py:66-94,
+ *                             landscape_only=True at spann3r/model.py:222) gives the value encoder the map with
+ *                             axes 1, 2 swapped; read it that way (patch grid W/16 x H/16), no copy
+ *   S3R_VALUE_ROPE            Spann3R(mem_pos_enc=True): RoPE inside the value encoder's blocks (spann3r/model.py:231) */
+#define S3R_VALUE_PTS_TRANSPOSED 1
+#define S3R_VALUE_ROPE 2
+int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, int flags, float* out, void* stream);
 /* spann3r/model.py:145-183 memory_read (eval: thresh = 5e-4; 0 disables): out = attn.V + feat; bank.attn += colsum */
 int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float* out,
                            void* stream);

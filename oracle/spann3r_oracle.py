@@ -200,6 +200,18 @@ def dpt_head(sd, name, dec, H, W, return_raw=False):
     return postprocess(out)
 
 
+def downstream_head(sd, name, dec, H, W):
+    """AsymmetricCroCo3DStereo.head{1,2} = transpose_to_landscape(head, activate=landscape_only=True)
+    (dust3r/model.py:128-129, spann3r/model.py:222; wrapper_yes, dust3r/utils/misc.py:66-94).  With the
+    PatchEmbedDust3R that load_model substitutes (dust3r/model.py:33) the tokens keep the image's own (H/16, W/16)
+    grid, so for a portrait frame the wrapper calls head(decout, (max, min)) = the true (H, W) and then swaps axes
+    1 and 2 of every output: callers -- and the value encoder -- see a [B, W, H, ...] landscape map."""
+    res = dpt_head(sd, name, dec, H, W)
+    if H > W:
+        res = {k: v.swapaxes(1, 2) for k, v in res.items()}
+    return res
+
+
 def postprocess(out):
     """dust3r/heads/postprocess.py:10-58 with depth_mode=('exp',-inf,inf), conf_mode=('exp',1,inf)."""
     fmap = out.permute(0, 2, 3, 1)
@@ -302,17 +314,18 @@ def key_head(sd, num, feat, dec_last):
     return linear(sd, f"attn_head_{num}.2", x)
 
 
-def encode_cur_value(sd, pts3d):
-    """spann3r/model.py:305-320 (use_feat=False, mem_pos_enc=False: no RoPE in the value encoder)."""
+def encode_cur_value(sd, pts3d, mem_pos_enc=False):
+    """spann3r/model.py:305-320 (use_feat=False).  mem_pos_enc (ctor flag, :228-235) puts dust3r's RoPE into the
+    value encoder's blocks, with the positions pos_patch_embed returns for the pointmap it is given."""
     x, pos = patch_embed(sd, "pos_patch_embed", pts3d.permute(0, 3, 1, 2))
     for i in range(6):
-        x = block(sd, f"value_encoder.{i}", x, pos, 16, use_rope=False)
+        x = block(sd, f"value_encoder.{i}", x, pos, 16, use_rope=mem_pos_enc)
     x = layernorm(sd, "value_norm", x, 1e-6)
     return linear(sd, "value_out", x)
 
 
 @torch.no_grad()
-def forward(sd, frames, return_memory=False, trace=None, **mem_kw):
+def forward(sd, frames, return_memory=False, trace=None, mem_pos_enc=False, **mem_kw):
     """Spann3R.forward in eval mode, spann3r/model.py:473-539.  frames: list of {'img': [B,3,H,W]}."""
     sp_mem = SpatialMemory(sd, **mem_kw)
     feat1 = feat2 = pos1 = pos2 = None
@@ -331,9 +344,9 @@ def forward(sd, frames, return_memory=False, trace=None, **mem_kw):
         dec1, dec2 = decoder(sd, feat_fuse, pos1, feat2, pos2)
         feat_k1 = key_head(sd, 1, feat1, dec1[-1])
         feat_k2 = key_head(sd, 2, feat2, dec2[-1])
-        res1 = dpt_head(sd, "dust3r.downstream_head1", dec1, H, W)
-        res2 = dpt_head(sd, "dust3r.downstream_head2", dec2, H, W)
-        cur_v = encode_cur_value(sd, res1["pts3d"])
+        res1 = downstream_head(sd, "dust3r.downstream_head1", dec1, H, W)
+        res2 = downstream_head(sd, "dust3r.downstream_head2", dec2, H, W)
+        cur_v = encode_cur_value(sd, res1["pts3d"], mem_pos_enc)
         sp_mem.add_mem_check(feat_k1, cur_v + feat_k1)
         if trace is not None:
             trace.append(dict(feat1=feat1, feat2=feat2, feat_fuse=feat_fuse, dec1=dec1, dec2=dec2, feat_k1=feat_k1,
@@ -363,8 +376,8 @@ def dust3r_forward(sd, view1, view2):
     B, _, H, W = img1.shape
     feats, pos = encode_image(sd, torch.cat((img1, img2), dim=0))
     dec1, dec2 = decoder(sd, feats[:B], pos[:B], feats[B:], pos[B:])
-    res1 = dpt_head(sd, "dust3r.downstream_head1", dec1, H, W)
-    res2 = dpt_head(sd, "dust3r.downstream_head2", dec2, H, W)
+    res1 = downstream_head(sd, "dust3r.downstream_head1", dec1, H, W)
+    res2 = downstream_head(sd, "dust3r.downstream_head2", dec2, H, W)
     res2["pts3d_in_other_view"] = res2.pop("pts3d")
     return res1, res2
 
@@ -399,8 +412,8 @@ def offline_reconstruction(sd, frames, graph, **mem_kw):
     feat1, feat2 = out.chunk(2, dim=0)
     pos1, pos2 = pos.chunk(2, dim=0)
     dec1, dec2 = decoder(sd, feat1, pos1, feat2, pos2)
-    res1 = dpt_head(sd, "dust3r.downstream_head1", dec1, H, W)
-    res2 = dpt_head(sd, "dust3r.downstream_head2", dec2, H, W)
+    res1 = downstream_head(sd, "dust3r.downstream_head1", dec1, H, W)
+    res2 = downstream_head(sd, "dust3r.downstream_head2", dec2, H, W)
     feat_k2, preds, preds_all = None, None, []
     while True:
         if feat_k2 is not None:
@@ -410,8 +423,8 @@ def offline_reconstruction(sd, frames, graph, **mem_kw):
             for i in idx_todo:   # find_next_best_view
                 f2, ps2 = encode_image(sd, frames[i]["img"])
                 d1, d2 = decoder(sd, feat_fuse, pos1, f2, ps2)
-                r1 = dpt_head(sd, "dust3r.downstream_head1", d1, H, W)
-                r2 = dpt_head(sd, "dust3r.downstream_head2", d2, H, W)
+                r1 = downstream_head(sd, "dust3r.downstream_head1", d1, H, W)
+                r2 = downstream_head(sd, "dust3r.downstream_head2", d2, H, W)
                 total = conf_score(r1["conf"]) + conf_score(r2["conf"])
                 if total > best_conf:
                     best_conf, best = total, (i, d1, d2, r1, r2, f2, ps2)

@@ -86,6 +86,7 @@ struct s3r_engine {
 
   // lookup tables
   int* pos = nullptr;  // [max_rows, 2] (y, x)
+  int* pos_t = nullptr;  // [B*N, 2]: positions of the landscape-transposed grid (gw x gh), value encoder of portrait frames
   // encoder / value-encoder workspace (rows up to max_images*N, dim 1024)
   float* X = nullptr; Planes P, P2, Pim, AO, Hb; float *Qb = nullptr, *Kb = nullptr, *Vtb = nullptr;
   float2 *St1 = nullptr, *St2 = nullptr;   // LayerNorm chunk statistics of the residual stream (block input / after attention)
@@ -207,13 +208,15 @@ struct s3r_engine {
   // LayerNorms are folded into the GEMM that consumes them (s3r_lin.cs): on entry P holds the planes of the block
   // input x and St1 its per-row chunk statistics (written by whichever GEMM produced x); on exit likewise for
   // the block output.  No LayerNorm kernel runs inside a block.
-  int vit_block(PlanCache& pc, const s3r_block_w& bw, int D, int nimg, bool rope, float* Xp, cudaStream_t st) {
+  int vit_block(PlanCache& pc, const s3r_block_w& bw, int D, int nimg, bool rope, float* Xp, cudaStream_t st,
+                const int* pos_tab = nullptr) {
     const int rows = nimg * N, heads = D / 64;
+    if (!pos_tab) pos_tab = pos;
     int r;
     {
       Geom g; g.W = rows; g.Kc = D; g.N = 3 * D;
       Epi e; e.epi = EPI_QKV; e.bias = bw.qkv.b; e.q_C = D; e.q_role_base = 0; e.q_ntok = N; e.q_ntok_pad = Npad;
-      e.q_rope = rope ? 1 : 0; e.q_nb = nimg; e.q_pos = pos; e.q_cs = (const float2*)w.rope_cs;
+      e.q_rope = rope ? 1 : 0; e.q_nb = nimg; e.q_pos = pos_tab; e.q_cs = (const float2*)w.rope_cs;
       e.q_out = Qb; e.k_out = Kb; e.vt_out = Vtb; e.q_scale = 0.125f;
       e.ln_stats = St1; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.qkv.cs;                       // norm1
       if ((r = gemm(pc, P, WP(bw.qkv.w), g, e, st))) return r;
@@ -282,6 +285,7 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
   const size_t N = e->N, R = (size_t)batch * N, Mx = (size_t)max_images * N;
   const size_t rows_max = Mx > 2 * R ? Mx : 2 * R;
   e->pos = e->alloc<int>(rows_max * 2);
+  e->pos_t = e->alloc<int>(R * 2);
   // encoder / value encoder
   e->X = e->alloc<float>(Mx * 1024);
   e->P = e->alloc_planes(Mx * 1024);
@@ -364,6 +368,7 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
     return nullptr;
   }
   fill_pos_kernel<<<(unsigned)((rows_max + 255) / 256), 256>>>(e->pos, (long long)rows_max, e->N, e->gw);
+  fill_pos_kernel<<<(unsigned)((R + 255) / 256), 256>>>(e->pos_t, (long long)R, e->N, e->gh);
   if (cudaDeviceSynchronize() != cudaSuccess) {
     set_error("s3r_engine_create: init kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     s3r_engine_destroy(e);
@@ -709,17 +714,28 @@ int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
 // value encoder: spann3r/model.py:305-320 (pos_patch_embed on pts3d, 6 Blocks without RoPE, value_norm,
 // value_out) + `cur_v + feat_k1` (:519-521) fused as the residual of value_out.
 // ------------------------------------------------------------------------------------------------
-int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, float* out, void* stream) {
+int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, int flags, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (flags & ~(S3R_VALUE_PTS_TRANSPOSED | S3R_VALUE_ROPE)) {
+    set_error("s3r_engine_value: unknown flags 0x%x", flags);
+    return -1;
+  }
+  const bool tr = (flags & S3R_VALUE_PTS_TRANSPOSED) != 0, rope = (flags & S3R_VALUE_ROPE) != 0;
+  // the cached plans do not depend on the flags: same launches, shapes and buffers; the flags only pick the im2col
+  // strides and the per-call RoPE switch / position table of the qkv epilogue
   PlanCache& pc = e->pc_value;
   pc.begin();
   const int B = e->B;
   const int rows = B * e->N;
   int r;
   ++e->launches;
-  // pts3d is [B, H, W, 3]: the reference permutes to NCHW first; here the im2col reads it with NHWC strides
-  if ((r = launch_im2col_patch16(pts3d, (long long)e->H * e->W * 3, 1, (long long)e->W * 3, 3, B, e->gh, e->gw, e->Pim.hi,
-                                 e->Pim.lo, st)))
+  // pts3d is the head's [B, H, W, 3] map: the reference permutes to NCHW first; here the im2col reads it with NHWC
+  // strides.  For a portrait frame the landscape wrapper (dust3r/utils/misc.py:66-94) hands encode_cur_value the
+  // map with axes 1 and 2 swapped, i.e. an image of W rows x H columns: same memory, row / column strides exchanged,
+  // patch grid gw x gh (S3R_VALUE_PTS_TRANSPOSED).
+  const long long srow = (long long)e->W * 3, spx = 3;
+  if ((r = launch_im2col_patch16(pts3d, (long long)e->H * e->W * 3, 1, tr ? spx : srow, tr ? srow : spx, B,
+                                 tr ? e->gw : e->gh, tr ? e->gh : e->gw, e->Pim.hi, e->Pim.lo, st)))
     return r;
   {
     Geom g; g.W = rows; g.Kc = 768; g.N = 1024;
@@ -728,7 +744,7 @@ int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, fl
     if ((r = e->gemm(pc, e->Pim, WP(e->w.pos_patch_embed.w), g, ep, st))) return r;
   }
   for (int l = 0; l < 6; ++l)
-    if ((r = e->vit_block(pc, e->w.val[l], 1024, B, false, e->Xv, st))) return r;
+    if ((r = e->vit_block(pc, e->w.val[l], 1024, B, rope, e->Xv, st, tr ? e->pos_t : e->pos))) return r;
   if ((r = e->ln(e->Xv, e->w.value_norm, 0, 0, 1e-6f, rows, 1024, nullptr, 0, e->Pv, 1024, 0, 0, st))) return r;
   {
     Geom g; g.W = rows; g.Kc = 1024; g.N = 1024;

@@ -75,7 +75,7 @@ _lib.register_protos({
     "s3r_engine_decode": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "s3r_engine_keyheads": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "s3r_engine_heads": (_i, [_vp, _vp, _vp, _vp]),
-    "s3r_engine_value": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "s3r_engine_value": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "s3r_engine_memory_read": (_i, [_vp, C.POINTER(Bank), _vp, _f, _vp, _vp]),
     "s3r_engine_memory_append": (_i, [_vp, C.POINTER(Bank), _vp, _vp, _vp]),
     "s3r_engine_check_sim": (_i, [_vp, C.POINTER(Bank), _vp, _i, _vp, _vp]),
@@ -87,6 +87,7 @@ _lib.register_protos({
 })
 
 ROPE_MAXPOS = 64
+VALUE_PTS_TRANSPOSED, VALUE_ROPE = 1, 2   # include/spann3r_b200.h: flags of s3r_engine_value
 
 
 def rope_cs_table(maxpos: int = ROPE_MAXPOS, base: float = 100.0) -> torch.Tensor:
@@ -350,10 +351,13 @@ class Engine:
         _lib.check(_lib.lib().s3r_engine_heads(self._h, _lib.ptr(pts), _lib.ptr(conf), _lib.stream_ptr()), "heads")
         return pts, conf
 
-    def value(self, pts3d, feat_k1):
+    def value(self, pts3d, feat_k1, transposed: bool = False, rope: bool = False):
+        """pts3d: head 1's map in the head's own [B, H, W, 3] layout; transposed=True reads it as the [B, W, H, 3]
+        landscape view the reference's head wrapper returns for portrait frames (S3R_VALUE_PTS_TRANSPOSED)."""
         self._chk(pts3d, (self.B, self.H, self.W, 3)); self._chk(feat_k1, (self.B, self.N, 1024))
         out = self._new(self.B, self.N, 1024)
-        _lib.check(_lib.lib().s3r_engine_value(self._h, _lib.ptr(pts3d), _lib.ptr(feat_k1), _lib.ptr(out),
+        flags = (VALUE_PTS_TRANSPOSED if transposed else 0) | (VALUE_ROPE if rope else 0)
+        _lib.check(_lib.lib().s3r_engine_value(self._h, _lib.ptr(pts3d), _lib.ptr(feat_k1), flags, _lib.ptr(out),
                                                _lib.stream_ptr()), "value")
         return out
 

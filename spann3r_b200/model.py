@@ -9,7 +9,8 @@ The modules below hold parameters only.  All arithmetic runs in libspann3r_b200.
 `engine.Engine`; there is no eager-PyTorch, CPU or Triton path -- on a machine without an sm_100
 GPU `forward` raises.  Inference (eval mode) only: the training-mode branches of the reference
 (memory dropout, attn_thresh=0, autograd) are out of scope this round.
-`offline_reconstruction` is built on the same engine stages.
+`offline_reconstruction` is built on the same engine stages.  Portrait frames follow the
+reference's landscape wrapper (`_to_landscape`); `mem_pos_enc=True` is supported, `use_feat=True` is not.
 """
 from __future__ import annotations
 
@@ -53,6 +54,13 @@ def build_param_tree(root: nn.Module, keys_shapes: dict, prefix: str = ""):
             shared[canon] = nn.Parameter(torch.empty(tuple(shape), dtype=torch.float32), requires_grad=False)
         mod.register_parameter(parts[-1], shared[canon])
     return root
+
+
+def _to_landscape(t: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """transpose_to_landscape / wrapper_yes (dust3r/utils/misc.py:66-94) as Spann3R configures it (landscape_only=True,
+    spann3r/model.py:222) over PatchEmbedDust3R tokens: the head runs at the frame's own (H, W); for a portrait
+    frame every output then has axes 1 and 2 swapped -- a VIEW, like the reference's `swapaxes`."""
+    return t.swapaxes(1, 2) if H > W else t
 
 
 class AsymmetricCroCo3DStereo(ParamModule):
@@ -101,7 +109,8 @@ class AsymmetricCroCo3DStereo(ParamModule):
         feats = eng.encode(torch.cat((img1, img2), dim=0).contiguous())
         eng.decode(feats[:B].contiguous(), feats[B:].contiguous())
         pts, conf = eng.heads()
-        return ({"pts3d": pts[0], "conf": conf[0]}, {"pts3d_in_other_view": pts[1], "conf": conf[1]})
+        return ({"pts3d": _to_landscape(pts[0], H, W), "conf": _to_landscape(conf[0], H, W)},
+                {"pts3d_in_other_view": _to_landscape(pts[1], H, W), "conf": _to_landscape(conf[1], H, W)})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,9 +245,9 @@ class Spann3R(ParamModule):
     def __init__(self, dus3r_name="./checkpoints/DUSt3R_ViTLarge_BaseDecoder_512_dpt.pth", use_feat=False,
                  mem_pos_enc=False, memory_dropout=0.15, max_encode_batch: int = 16):
         super().__init__()
-        if use_feat or mem_pos_enc:
-            raise NotImplementedError("use_feat=True / mem_pos_enc=True variants are not built (the released "
-                                      "checkpoints and demo.py/eval.py use the defaults)")
+        if use_feat:
+            raise NotImplementedError("use_feat=True (a 768-wide value encoder fed with decoder tokens, 48-wide heads) is "
+                                      "not built; the released checkpoints and demo.py / eval.py use the default")
         self.use_feat, self.mem_pos_enc = use_feat, mem_pos_enc
         spec = synth.load_spec()
         self.dust3r = AsymmetricCroCo3DStereo(spec)
@@ -304,6 +313,17 @@ class Spann3R(ParamModule):
         dev = next(self.parameters()).device
         return t.to(dev, torch.float32, non_blocking=True).contiguous()
 
+    @staticmethod
+    def _check_true_shape(frames, H, W):
+        """The reference takes (H, W) from view['true_shape'] when present (spann3r/model.py:263-287); with the
+        PatchEmbedDust3R it runs, that is the tensor's own shape for every frame a dataset produces."""
+        for f in frames:
+            if tuple(f["img"].shape[-2:]) != (H, W):
+                raise ValueError("all frames of a sequence must have the same height and width")
+            ts = f.get("true_shape")
+            if ts is not None and any((int(h), int(w)) != (H, W) for h, w in torch.as_tensor(ts).reshape(-1, 2).tolist()):
+                raise NotImplementedError(f"true_shape {ts} differs from the image tensor shape {(H, W)}")
+
     def _positions(self, B, H, W):
         key = (H, W)
         if key not in self._pos_cache:
@@ -321,8 +341,8 @@ class Spann3R(ParamModule):
         F_ = len(frames)
         img0 = frames[0]["img"]
         B, _, H, W = img0.shape
-        if H > W:
-            raise NotImplementedError("portrait inputs (transpose_to_landscape, dust3r/utils/misc.py:66-94) not built")
+        self._check_true_shape(frames, H, W)
+        portrait = H > W        # heads run at (H, W); outputs and the value encoder's input are the landscape views
         eng = self._engine_for(B, H, W, n_frames=F_)
         sp_mem = SpatialMemory(engine=eng)
         N = eng.N
@@ -346,9 +366,10 @@ class Spann3R(ParamModule):
             feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
             sim = sp_mem.check_sim_async(feat_k1, thresh=sp_mem.sim_thresh)   # read back in add_mem_check below
             pts, conf = eng.heads()
-            res1 = {"pts3d": pts[0], "conf": conf[0]}
-            res2 = {"pts3d": pts[1], "conf": conf[1]}
-            mem_v = eng.value(res1["pts3d"], feat_k1)            # encode_cur_value(...) + feat_k1
+            res1 = {"pts3d": _to_landscape(pts[0], H, W), "conf": _to_landscape(conf[0], H, W)}
+            res2 = {"pts3d": _to_landscape(pts[1], H, W), "conf": _to_landscape(conf[1], H, W)}
+            # encode_cur_value(res1['pts3d']) + feat_k1; the engine reads pts[0] through the landscape view's strides
+            mem_v = eng.value(pts[0], feat_k1, transposed=portrait, rope=self.mem_pos_enc)
             sp_mem.add_mem_check(feat_k1, mem_v, sim_pending=sim)
             res2["pts3d_in_other_view"] = res2.pop("pts3d")
             if preds is None:
@@ -390,6 +411,8 @@ class Spann3R(ParamModule):
         n_frames = len(frames)
         idx_todo = list(range(n_frames))
         B, _, H, W = frames[0]["img"].shape
+        self._check_true_shape(frames, H, W)
+        portrait = H > W
         eng = self._engine_for(B, H, W, n_frames=n_frames)
         N = eng.N
         sp_mem = SpatialMemory(engine=eng)
@@ -408,7 +431,8 @@ class Spann3R(ParamModule):
         def decode_heads(f_fuse, f2):
             eng.decode(f_fuse, f2)
             pts, conf = eng.heads()
-            return ({"pts3d": pts[0], "conf": conf[0]}, {"pts3d": pts[1], "conf": conf[1]})
+            return ({"pts3d": _to_landscape(pts[0], H, W), "conf": _to_landscape(conf[0], H, W), "_raw": pts[0]},
+                    {"pts3d": _to_landscape(pts[1], H, W), "conf": _to_landscape(conf[1], H, W)})
 
         feat1, feat2 = feats[p0], feats[p1]
         feat_fuse = feat1
@@ -430,7 +454,7 @@ class Spann3R(ParamModule):
                 feat2 = feats[best_id]
                 res1, res2 = decode_heads(feat_fuse, feat2)          # restores the engine's hooks for the winner
             feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
-            mem_v = eng.value(res1["pts3d"], feat_k1)
+            mem_v = eng.value(res1.pop("_raw"), feat_k1, transposed=portrait, rope=self.mem_pos_enc)
             sp_mem.add_mem_check(feat_k1, mem_v)
             res2["pts3d_in_other_view"] = res2.pop("pts3d")
             if preds is None:

@@ -30,6 +30,9 @@ CASES = [
     ("cfg1_224_2f_raw.npz", False, 2, 224, 224),
     ("seq_224_4f_sharp.npz", True, 4, 224, 224),
     ("seq_384x512_3f_sharp.npz", True, 3, 384, 512),
+    # portrait frames: heads at (H, W), outputs / value-encoder input transposed to landscape (dust3r/utils/misc.py:66-94)
+    ("seq_288x224_4f_sharp.npz", True, 4, 288, 224),
+    ("seq_512x384_3f_sharp.npz", True, 3, 512, 384),
 ]
 
 
@@ -56,6 +59,42 @@ def test_forward_matches_reference_golden(models, fname, sharpen, nf, H, W):
     assert np.array_equal(mem.mem_count.cpu().numpy(), g["mem/mem_count"])
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, bad
+
+
+def test_mem_pos_enc_variant_matches_reference_golden():
+    """Spann3R(mem_pos_enc=True): RoPE inside the value encoder (spann3r/model.py:228-235) -- same state-dict keys,
+    different memory values from the second read on."""
+    from spann3r_b200 import Spann3R, synth
+    g = np.load(os.path.join(GOLDEN, "seq_224_3f_sharp_mempos.npz"))
+    m = Spann3R(dus3r_name=None, mem_pos_enc=True)
+    m.load_state_dict(get_state_dict(True), strict=True)
+    m = m.cuda().eval()
+    preds, _, mem = m(synth.make_frames(3, 224, 224), return_memory=True)
+    s = int(g["meta/px_stride"])
+    errs = {f"{i}/{k}": rel_l2(v[:, ::s, ::s].cpu(), g[f"preds/{i}/{k}"]) for i, p in enumerate(preds) for k, v in p.items()}
+    errs["mem_v"] = rel_l2(mem.mem_v[:, ::7, ::8].cpu(), g["mem/mem_v_sub"])
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    del m
+
+
+def test_portrait_pairwise_and_offline_shapes(models):
+    """`model.dust3r(view1, view2)` on portrait frames returns landscape-transposed maps like the reference's wrapped
+    heads; values against the oracle."""
+    from oracle import spann3r_oracle as orc
+    from spann3r_b200 import synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = models[True]
+    sd = {k: v.cuda() for k, v in get_state_dict(True).items()}
+    fr = synth.make_frames(2, 288, 224)
+    res1, res2 = m.dust3r({"img": fr[0]["img"]}, {"img": fr[1]["img"]})
+    r1, r2 = orc.dust3r_forward(sd, {"img": fr[0]["img"].cuda()}, {"img": fr[1]["img"].cuda()})
+    assert res1["pts3d"].shape == (1, 224, 288, 3) and res2["conf"].shape == (1, 224, 288)
+    for a, b in ((res1, r1), (res2, r2)):
+        assert set(a) == set(b)
+        for k in b:
+            assert rel_l2(a[k].cpu(), b[k].cpu()) < TOL, k
 
 
 def test_stagewise_vs_oracle(models):

@@ -58,6 +58,36 @@ def test_forward_matches_reference(fname, sharpen, nf, H, W):
     assert rel_l2(_sub_tokens(trace[0]["cur_v"]), g["act/value_out#0"]) < TOL
 
 
+# Portrait frames (the landscape wrapper transposes every head output, dust3r/utils/misc.py:66-94) and the
+# mem_pos_enc=True constructor variant (RoPE in the value encoder): real-reference runs without activation hooks.
+VARIANT_CASES = [
+    ("seq_288x224_4f_sharp.npz", 4, 288, 224, False),
+    ("seq_512x384_3f_sharp.npz", 3, 512, 384, False),
+    ("seq_224_3f_sharp_mempos.npz", 3, 224, 224, True),
+]
+
+
+@pytest.mark.parametrize("fname,nf,H,W,mem_pos_enc", VARIANT_CASES)
+def test_portrait_and_mempos_match_reference(fname, nf, H, W, mem_pos_enc):
+    g = np.load(os.path.join(GOLDEN, fname))
+    sd = get_state_dict(True)
+    frames = synth.make_frames(nf, H, W)
+    preds, preds_all, mem = orc.forward(sd, frames, return_memory=True, mem_pos_enc=mem_pos_enc)
+    s = int(g["meta/px_stride"])
+    for i, p in enumerate(preds):
+        assert set(p.keys()) == {k.split("/")[-1] for k in g.files if k.startswith(f"preds/{i}/")}
+        for k, v in p.items():
+            assert v.shape[1:3] == (min(H, W), max(H, W)), (k, v.shape)       # always landscape
+            assert rel_l2(v[:, ::s, ::s], g[f"preds/{i}/{k}"]) < TOL, (fname, i, k)
+    for i, (_, r2) in enumerate(preds_all):
+        for k, v in r2.items():
+            assert rel_l2(v[:, ::s, ::s], g[f"preds_all/{i}/res2/{k}"]) < TOL, (fname, i, k)
+    assert rel_l2(_sub_tokens(mem.mem_k), g["mem/mem_k_sub"]) < TOL
+    assert rel_l2(_sub_tokens(mem.mem_v), g["mem/mem_v_sub"]) < TOL
+    assert rel_l2(mem.mem_attn, g["mem/mem_attn"]) < 1e-4
+    assert np.array_equal(mem.mem_count.numpy(), g["mem/mem_count"])
+
+
 def test_state_dict_spec_counts(spec):
     keys = spec["spann3r"]
     assert len(keys) == 1101

@@ -14,6 +14,9 @@ Outputs
   tests/golden/seq_224_4f_sharp.npz   4 x 224x224, sharpened weights (two memory reads)
   tests/golden/seq_384x512_3f_sharp.npz  3 x 384x512, sharpened, outputs sub-sampled (::4, ::4)
   tests/golden/offline_224_4f_sharp.npz  offline mode: 4 x 224x224, complete pair graph -> offline_reconstruction
+  tests/golden/seq_288x224_4f_sharp.npz  PORTRAIT 4 x (H=288, W=224): transpose_to_landscape (dust3r/utils/misc.py:66-94), outputs (::2, ::2)
+  tests/golden/seq_512x384_3f_sharp.npz  PORTRAIT 3 x (H=512, W=384), outputs sub-sampled (::4, ::4)
+  tests/golden/seq_224_3f_sharp_mempos.npz  3 x 224x224 with Spann3R(mem_pos_enc=True) (RoPE inside the value encoder)
 Each npz also holds sub-sampled per-stage activations captured with forward hooks so that a
 parity failure can be localised to a stage.
 """
@@ -32,7 +35,7 @@ sys.path.insert(0, REPO)
 GOLD = os.path.join(REPO, "tests", "golden")
 
 
-def build_reference(seed=0, sharpen=False):
+def build_reference(seed=0, sharpen=False, mem_pos_enc=False):
     sys.path.insert(0, REF)
     torch.serialization.add_safe_globals([argparse.Namespace])
     from spann3r.model import Spann3R  # noqa  (reference)
@@ -56,7 +59,7 @@ def build_reference(seed=0, sharpen=False):
     dust3r_sd = synth.make_state_dict(spec, seed=seed, prefix="dust3r.")
     torch.save({"args": argparse.Namespace(model=synth.DUST3R_ARGS), "model": dust3r_sd}, tmp)
     t0 = time.time()
-    m = Spann3R(dus3r_name=tmp, use_feat=False)
+    m = Spann3R(dus3r_name=tmp, use_feat=False, mem_pos_enc=mem_pos_enc)
     sd = synth.make_state_dict(spec, seed=seed, sharpen=sharpen)
     missing = m.load_state_dict(sd, strict=True)
     print("reference built in %.1fs" % (time.time() - t0), missing)
@@ -171,8 +174,15 @@ def main():
         if args.only != "spec":
             run(m, synth.make_frames(2, 224, 224), os.path.join(GOLD, "cfg1_224_2f_raw.npz"))
         del m
-    if args.only in ("all", "seq224", "seq512", "offline"):
+    if args.only in ("all", "mempos"):
+        m = build_reference(sharpen=True, mem_pos_enc=True)
+        run(m, synth.make_frames(3, 224, 224), os.path.join(GOLD, "seq_224_3f_sharp_mempos.npz"), px_stride=2, hooks=False)
+        del m
+    if args.only in ("all", "seq224", "seq512", "offline", "portrait"):
         m = build_reference(sharpen=True)
+        if args.only in ("all", "portrait"):
+            run(m, synth.make_frames(4, 288, 224), os.path.join(GOLD, "seq_288x224_4f_sharp.npz"), px_stride=2, hooks=False)
+            run(m, synth.make_frames(3, 512, 384), os.path.join(GOLD, "seq_512x384_3f_sharp.npz"), px_stride=4, hooks=False)
         if args.only in ("all", "offline"):
             run_offline(m, synth.make_frames(4, 224, 224), os.path.join(GOLD, "offline_224_4f_sharp.npz"))
         if args.only in ("all", "seq224"):
