@@ -152,6 +152,21 @@ int s3r_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int
 int s3r_focal_weiszfeld(const float* pts3d, int b, int h, int w, float ppx, float ppy, int iters, float lo, float hi,
                         float* scratch, float* focal, void* stream);
 
+/* ---- post-path geometry, second step: camera pose from a pointmap ----------------------------------------------------
+ * Replaces `cv2.solvePnPRansac(pts.reshape(-1,3), pixel grid, intrinsic, zeros(4))` of demo.py:166-180 (one CPU call per
+ * frame on a host copy of the pointmap), batched over b frames and entirely on the device: P3P hypotheses from
+ * n_samples minimal samples (cv2's iterationsCount; counter-based hash of `seed`), inlier counts at `reproj_err` px
+ * (cv2's default 8.0) over all n points, then `refine_iters` damped Gauss-Newton rounds on the best model's inliers
+ * (cv2's final SOLVEPNP_ITERATIVE refinement solves the same least-squares problem).
+ *   pts3d [b, n, 3] fp32; img_pts [b, n, 2] fp32 or NULL = the dense pixel grid (u = i % width, v = i / width);
+ *   out [b, 18] fp64: R (9, row-major, x_cam = R x + t), t (3), rvec (3, Rodrigues), inlier count of the RANSAC model,
+ *   RMS reprojection error after refinement (px), success (1/0);  inlier_mask [b, n] uint8 (cv2's `inliers`, as a mask);
+ *   workspace: s3r_pnp_workspace_bytes(b, n_samples) bytes, 16-byte aligned.  Deterministic for a given seed. */
+size_t s3r_pnp_workspace_bytes(int b, int n_samples);
+int s3r_pnp_ransac(const float* pts3d, const float* img_pts, int b, int64_t n, int width, double fx, double fy, double cx,
+                   double cy, float reproj_err, int n_samples, int refine_iters, uint64_t seed, void* workspace,
+                   double* out, uint8_t* inlier_mask, void* stream);
+
 /* ---- model level: the per-frame forward path -------------------------------------------------
  * Packed weights.  The host (spann3r_b200/weights.py) converts the reference state dict ONCE into
  * split-bf16 planes laid out [groups*N, taps*Kc] (K contiguous) plus fp32 biases / LayerNorm params,

@@ -159,6 +159,17 @@ int s3r_focal_weiszfeld(const float* pts3d, int b, int h, int w, float ppx, floa
   return launch_focal_weiszfeld(pts3d, b, h, w, ppx, ppy, iters, lo, hi, scratch, focal, S(stream));
 }
 
+size_t s3r_pnp_workspace_bytes(int b, int n_samples) {
+  if (b <= 0 || n_samples <= 0) return 0;
+  return pnp_workspace_bytes(b, n_samples);
+}
+int s3r_pnp_ransac(const float* pts3d, const float* img_pts, int b, int64_t n, int width, double fx, double fy, double cx,
+                   double cy, float reproj_err, int n_samples, int refine_iters, uint64_t seed, void* workspace,
+                   double* out, uint8_t* inlier_mask, void* stream) {
+  return launch_pnp_ransac(pts3d, img_pts, b, n, width, fx, fy, cx, cy, reproj_err, n_samples, refine_iters, seed,
+                           workspace, out, inlier_mask, S(stream));
+}
+
 int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, void* stream) {
   return launch_conf_score(conf, n, scratch256, out, S(stream));
 }

@@ -66,6 +66,12 @@ int launch_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const 
 int launch_focal_weiszfeld(const float* pts3d, int B, int H, int W, float ppx, float ppy, int iters, float lo, float hi,
                            float* scratch, float* focal, cudaStream_t st);
 
+// post-path geometry (pnp.cu): batched P3P-RANSAC + Gauss-Newton camera pose from a pointmap (cv2.solvePnPRansac of demo.py)
+size_t pnp_workspace_bytes(int B, int n_samples);
+int launch_pnp_ransac(const float* pts3d, const float* img_pts, int B, long long n, int width, double fx, double fy,
+                      double cx, double cy, float reproj_err, int n_samples, int refine_iters, unsigned long long seed,
+                      void* workspace, double* out, unsigned char* inlier_mask, cudaStream_t st);
+
 int launch_conf_score(const float* conf, long long n, float* scratch256, float* out, cudaStream_t st);
 
 // fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output

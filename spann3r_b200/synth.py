@@ -126,3 +126,40 @@ def make_frames(n_frames: int, height: int, width: int, batch: int = 1, seed0: i
         img = torch.rand((batch, 3, height, width), generator=g, dtype=torch.float32) * 2.0 - 1.0
         frames.append({"img": img})
     return frames
+
+
+def make_pointmap_case(height: int, width: int, focal: float, rvec, tvec, noise: float, outlier_frac: float, seed: int):
+    """A synthetic world-frame pointmap for the post-path geometry tests / bench (numpy): a smooth depth surface seen by a
+    pinhole camera (focal, principal point at the image centre) whose pose is x_cam = R(rvec) x_world + tvec, with
+    Gaussian noise on the points and a fraction of gross outliers.  Returns (pts3d [H, W, 3] float32, K [3, 3] float64)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    u, v = np.meshgrid(np.arange(width), np.arange(height))
+    K = np.array([[focal, 0, width / 2], [0, focal, height / 2], [0, 0, 1]], np.float64)
+    d = 2 + 0.5 * np.sin(u / 50.0) + 0.3 * np.cos(v / 40.0)
+    xc = np.stack(((u - width / 2) / focal * d, (v - height / 2) / focal * d, d), -1).reshape(-1, 3)
+    r = np.asarray(rvec, np.float64)
+    th = float(np.linalg.norm(r))
+    if th < 1e-12:
+        R = np.eye(3)
+    else:
+        kx, ky, kz = r / th
+        Kx = np.array([[0, -kz, ky], [kz, 0, -kx], [-ky, kx, 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    xw = (xc - np.asarray(tvec, np.float64)) @ R          # x_cam = R x_world + t  =>  x_world = R^T (x_cam - t)
+    xw += rng.normal(0, noise, xw.shape)
+    n_out = int(outlier_frac * len(xw))
+    if n_out:
+        idx = rng.choice(len(xw), n_out, replace=False)
+        xw[idx] += rng.normal(0, 0.5, (n_out, 3))
+    return xw.astype(np.float32).reshape(height, width, 3), K
+
+
+# (height, width, focal, rvec, tvec, noise, outlier_frac, seed): the cases of tests/golden/pnp.json
+PNP_CASES = [
+    (384, 512, 400.0, (0.1, -0.2, 0.05), (0.3, -0.1, 0.2), 0.002, 0.0, 1),
+    (384, 512, 450.0, (0.3, 0.2, -0.1), (-0.5, 0.2, 0.4), 0.005, 0.2, 2),
+    (224, 224, 250.0, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), 0.001, 0.1, 3),
+    (384, 512, 420.0, (-0.2, 0.4, 0.3), (0.1, 0.6, -0.3), 0.003, 0.3, 4),
+    (384, 512, 380.0, (0.05, 1.2, -0.4), (1.0, -0.3, 0.8), 0.004, 0.45, 5),
+]
