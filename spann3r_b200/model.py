@@ -256,6 +256,12 @@ class Spann3R(ParamModule):
         build_param_tree(self, rest)
         self.memory_dropout = memory_dropout
         self.max_encode_batch = max_encode_batch
+        # EXPERIMENT, off by default and not yet measured on a B200: encode frame i+2 on a low-priority side
+        # stream (own engine = own workspace) while the latency-bound decode / heads / value chain of step i runs on a
+        # high-priority stream, instead of encoding the whole sequence up front.  Same arithmetic per frame.
+        self.overlap_encoder = os.environ.get("S3R_ENC_OVERLAP", "0") == "1"
+        self._enc_engines = {}
+        self._streams = None
         self._packed = None
         self._packed_version = None
         self._engines = {}
@@ -292,6 +298,7 @@ class Spann3R(ParamModule):
             if dev.type != "cuda":
                 raise RuntimeError("spann3r_b200.Spann3R runs on a B200 only: call .to('cuda') first (no CPU path)")
             self._engines.clear()
+            self._enc_engines.clear()
             self._packed = None
             self._packed = PackedWeights(self.state_dict(), device=dev)
             self._packed_version = v
@@ -342,7 +349,6 @@ class Spann3R(ParamModule):
         img0 = frames[0]["img"]
         B, _, H, W = img0.shape
         self._check_true_shape(frames, H, W)
-        portrait = H > W        # heads run at (H, W); outputs and the value encoder's input are the landscape views
         eng = self._engine_for(B, H, W, n_frames=F_)
         sp_mem = SpatialMemory(engine=eng)
         N = eng.N
@@ -350,17 +356,77 @@ class Spann3R(ParamModule):
         # The encoder has no dependence on the memory loop: encode every frame up front in large batches
         # (SURVEY.md §3.1); per-image results are identical to the reference's pair / single-frame calls.
         imgs = [self._dev(f["img"]) for f in frames]
+        if self.overlap_encoder and F_ > 2:
+            return self._forward_overlapped(frames, imgs, eng, sp_mem, return_memory)
         feats = []
         chunk = max(1, eng.max_images // B)
         for s in range(0, F_, chunk):
             part = imgs[s: s + chunk]
             out = eng.encode(torch.cat(part, dim=0) if len(part) > 1 else part[0])
             feats += list(out.view(len(part), B, N, 1024).unbind(0))
+        return self._frame_loop(F_, H, W, eng, sp_mem, lambda i: feats[i], return_memory)
 
+    def _forward_overlapped(self, frames, imgs, eng, sp_mem, return_memory):
+        """S3R_ENC_OVERLAP=1 (experiment): frames 0, 1 are encoded on the decode stream; frame i+2 is encoded by a second
+        engine (own workspace, shared weights) on a low-priority stream while step i runs; step i+1 waits on its event."""
+        F_ = len(frames)
+        B, _, H, W = imgs[0].shape
+        N = eng.N
+        key = (B, H, W)
+        enc = self._enc_engines.get(key)
+        if enc is None:
+            enc = self._enc_engines[key] = Engine(self._weights(), B, H, W, max_images=2 * B)
+        if self._streams is None:
+            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            self._streams = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=lo))   # (decode chain, encoder)
+        dec_s, enc_s = self._streams
+        caller = torch.cuda.current_stream()
+        dec_s.wait_stream(caller)
+        enc_s.wait_stream(caller)
+        feats, ready = {}, {}
+
+        def enqueue_encode(j):
+            with torch.cuda.stream(enc_s):
+                f = enc.encode(imgs[j])
+                ev = torch.cuda.Event()
+                ev.record(enc_s)
+            f.record_stream(dec_s)
+            feats[j], ready[j] = f, ev
+
+        def feat_of(j):
+            """The frame loop asks for (i, i + 1) at the top of step i: start the NEXT frame's encoder before this step's
+            work is enqueued, then make the decode stream wait for frame j if it came from the side stream."""
+            if j + 1 < F_ and (j + 1) not in feats:
+                enqueue_encode(j + 1)
+            ev = ready.pop(j, None)
+            if ev is not None:
+                dec_s.wait_event(ev)
+            return feats[j]
+
+        with torch.cuda.stream(dec_s):
+            first = eng.encode(torch.cat(imgs[:2], dim=0)).view(2, B, N, 1024)
+            feats[0], feats[1] = first[0], first[1]
+            out = self._frame_loop(F_, H, W, eng, sp_mem, feat_of, return_memory)
+        caller.wait_stream(dec_s)
+        caller.wait_stream(enc_s)
+        for p in out[0]:                         # results were allocated on dec_s and are consumed on the caller's stream
+            for t in p.values():
+                t.record_stream(caller)
+        for _, r2 in out[1]:
+            for t in r2.values():
+                t.record_stream(caller)
+        if sp_mem.bank is not None:
+            for name in ("kn_hi", "kn_lo", "vnt_hi", "vnt_lo", "k_raw", "v_raw", "attn", "count"):
+                getattr(sp_mem.bank, name).record_stream(caller)
+        return out
+
+    def _frame_loop(self, F_, H, W, eng, sp_mem, feat_of, return_memory):
+        """The frame loop of spann3r/model.py:484-533 over already (or concurrently) encoded frames."""
+        portrait = H > W        # heads run at (H, W); outputs and the value encoder's input are the landscape views
         feat_k2 = None
         preds, preds_all = None, []
         for i in range(F_ - 1):
-            feat1, feat2 = feats[i], feats[i + 1]
+            feat1, feat2 = feat_of(i), feat_of(i + 1)
             feat_fuse = sp_mem.memory_read(feat_k2, res=True) if feat_k2 is not None else feat1
             eng.decode(feat_fuse, feat2)
             feat_k1, feat_k2 = eng.keyheads(feat1, feat2)
