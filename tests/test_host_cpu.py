@@ -114,3 +114,122 @@ def test_layernorm_fold_algebra():
     out = rstd[:, None] * acc - (rstd * mean)[:, None] * cs[None, :] + bf[None, :]
     err = float((out.double() - ref).norm() / ref.norm())
     assert err < 2e-6, err
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Host control flow of Spann3R.forward / offline_reconstruction over a FAKE engine (shapes only, no arithmetic): the
+# frame loop, the dict keys / shapes of spann3r/model.py:473-539, the landscape views of portrait frames, which pointmap
+# the value stage is handed, and the memory bookkeeping -- everything the Python layer decides, checked without a GPU.
+# ------------------------------------------------------------------------------------------------------------------
+class _FakeEngine:
+    def __init__(self, B, H, W):
+        self.B, self.H, self.W, self.N = B, H, W, (H // 16) * (W // 16)
+        self.device, self.max_images, self.calls = torch.device("cpu"), 64, []
+
+    def encode(self, img):
+        self.calls.append(("encode", img.shape[0]))
+        return torch.full((img.shape[0], self.N, 1024), 1.0) * img.mean(dim=(1, 2, 3))[:, None, None]
+
+    def decode(self, f1, f2, want_all=False):
+        assert f1.shape == f2.shape == (self.B, self.N, 1024)
+        self.calls.append(("decode",))
+        return torch.zeros(12, 2, self.B, self.N, 768) if want_all else None
+
+    def keyheads(self, f1, f2):
+        return f1 + 1, f2 + 2
+
+    def heads(self):
+        self.calls.append(("heads",))
+        pts = torch.arange(2 * self.B * self.H * self.W * 3, dtype=torch.float32).view(2, self.B, self.H, self.W, 3)
+        return pts, torch.ones(2, self.B, self.H, self.W) * 2
+
+    def value(self, pts3d, feat_k1, transposed=False, rope=False):
+        assert pts3d.is_contiguous() and pts3d.shape == (self.B, self.H, self.W, 3)     # head layout, never the view
+        self.calls.append(("value", transposed, rope))
+        return feat_k1 * 0
+
+    def memory_read(self, bank, feat, thresh):
+        self.calls.append(("read", bank.len))
+        return feat
+
+    def memory_append(self, bank, k, v):
+        bank.len += self.N
+
+    def check_sim(self, bank, feat_k, wm):
+        return torch.zeros(self.B, wm)
+
+
+def _fake_model(monkeypatch, mem_pos_enc=False):
+    from spann3r_b200 import Spann3R
+    from spann3r_b200 import model as M
+    m = Spann3R(dus3r_name=None, mem_pos_enc=mem_pos_enc).eval()
+    engines = {}
+
+    def engine_for(B, H, W, n_frames=2, encode_only=False):
+        m._hw = (H, W)
+        return engines.setdefault((B, H, W), _FakeEngine(B, H, W))
+
+    monkeypatch.setattr(m, "_engine_for", engine_for)
+    monkeypatch.setattr(M.SpatialMemory, "check_sim_async", lambda self, feat_k, thresh=0.7: None)
+    return m, engines
+
+
+@pytest.mark.parametrize("H,W", [(64, 96), (96, 64)])
+def test_forward_control_flow_on_a_fake_engine(monkeypatch, H, W):
+    from spann3r_b200 import synth
+    m, engines = _fake_model(monkeypatch, mem_pos_enc=(H > W))
+    F_ = 5
+    frames = synth.make_frames(F_, H, W)
+    frames[0]["true_shape"] = torch.tensor([[H, W]], dtype=torch.int32)
+    preds, preds_all, mem = m(frames, return_memory=True)
+    eng = engines[(1, H, W)]
+    lh, lw = min(H, W), max(H, W)
+    assert len(preds) == F_ and len(preds_all) == F_ - 1
+    assert set(preds[0]) == {"pts3d", "conf"}
+    for p in preds[1:]:
+        assert set(p) == {"pts3d_in_other_view", "conf"}
+    for p in preds:
+        for k, v in p.items():
+            assert v.shape[:3] == (1, lh, lw), (k, v.shape)                      # always landscape (misc.py:66-94)
+    # a portrait output is the axis-swapped VIEW of what the head wrote
+    raw = eng.heads()[0]
+    exp = raw[0].swapaxes(1, 2) if H > W else raw[0]
+    assert torch.equal(preds[0]["pts3d"], exp)
+    assert torch.equal(preds[-1]["pts3d_in_other_view"], raw[1].swapaxes(1, 2) if H > W else raw[1])
+    assert preds_all[0][0] is preds[0] and preds_all[-1][1] is preds[-1]
+    # one batched encode, then per step: (read from step 1 on) decode, heads, value with the right flags
+    assert eng.calls[0] == ("encode", F_)
+    steps = [c for c in eng.calls if c[0] in ("read", "decode", "value")]
+    assert [c[0] for c in steps[:3]] == ["decode", "value", "read"]
+    assert all(c == ("value", H > W, H > W) for c in steps if c[0] == "value")   # transposed read; rope = mem_pos_enc
+    assert [c[1] for c in steps if c[0] == "read"] == [eng.N * i for i in range(1, F_ - 1)]
+    assert mem.wm == F_ - 1 and mem.bank.len == eng.N * (F_ - 1) and mem.lm == 0
+    assert mem.mem_k.shape == (1, eng.N * (F_ - 1), 1024) and mem.mem_count.shape == (1, eng.N * (F_ - 1), 1)
+    # inconsistent inputs are rejected, not silently reshaped
+    bad = synth.make_frames(2, H, W)
+    bad[1]["true_shape"] = torch.tensor([[W, H]])
+    with pytest.raises(NotImplementedError):
+        m(bad)
+    with pytest.raises(ValueError):
+        m([synth.make_frames(1, H, W)[0], synth.make_frames(1, W, H)[0]])
+
+
+def test_pairwise_and_offline_control_flow_on_a_fake_engine(monkeypatch):
+    from spann3r_b200 import synth
+    from spann3r_b200 import model as M
+    H, W = 96, 64
+    m, engines = _fake_model(monkeypatch)
+    monkeypatch.setattr(M, "_conf_score", lambda c: c.mean())
+    fr = synth.make_frames(4, H, W)
+    r1, r2 = m.dust3r(fr[0], fr[1])
+    assert set(r1) == {"pts3d", "conf"} and set(r2) == {"pts3d_in_other_view", "conf"}
+    assert r1["pts3d"].shape == (1, W, H, 3) and r2["conf"].shape == (1, W, H)
+    graph = {"view1": {"idx": [0, 1, 2, 3]}, "view2": {"idx": [1, 2, 3, 0]},
+             "pred1": {"conf": torch.tensor([2.0, 5.0, 3.0, 2.5]).view(4, 1, 1).expand(4, 4, 4).contiguous()},
+             "pred2": {"conf": torch.ones(4, 4, 4) * 2}}
+    preds, preds_all, idx_used = m.offline_reconstruction(fr, graph)
+    assert idx_used[:2] == [1, 2] and sorted(idx_used) == [0, 1, 2, 3]
+    assert len(preds) == 4 and set(preds[0]) == {"pts3d", "conf"} and all("_raw" not in p for p in preds)
+    assert all(v.shape[1:3] == (W, H) for p in preds for v in p.values())
+    eng = engines[(1, H, W)]
+    assert all(c == ("value", True, False) for c in eng.calls if c[0] == "value")
