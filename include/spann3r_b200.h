@@ -152,6 +152,12 @@ int s3r_resample_v_u8_norm(const uint8_t* tmp, int cols, int out_rows, const int
 int s3r_focal_weiszfeld(const float* pts3d, int b, int h, int w, float ppx, float ppy, int iters, float lo, float hi,
                         float* scratch, float* focal, void* stream);
 
+/* The same function with focal_mode='median' (its default; dust3r/post_process.py:26-36): nanmedian of the 2*h*w per-pixel
+ * votes (u z / x, v z / y), i.e. an element of the vote set -- selected exactly by a 4 x 8-bit radix select on the fp32
+ * votes' ordered keys, so the result is bit-identical to the reference's.  scratch: b * 260 int32.  All-NaN votes -> NaN. */
+int s3r_focal_median(const float* pts3d, int b, int h, int w, float ppx, float ppy, float lo, float hi, int32_t* scratch,
+                     float* focal, void* stream);
+
 /* ---- post-path geometry, second step: camera pose from a pointmap ----------------------------------------------------
  * Replaces `cv2.solvePnPRansac(pts.reshape(-1,3), pixel grid, intrinsic, zeros(4))` of demo.py:166-180 (one CPU call per
  * frame on a host copy of the pointmap), batched over b frames and entirely on the device: P3P hypotheses from

@@ -57,6 +57,7 @@ _PROTOS = {
     "s3r_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "s3r_conf_score": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "s3r_focal_weiszfeld": (_i, [_vp, _i, _i, _i, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
+    "s3r_focal_median": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
     "s3r_pnp_workspace_bytes": (C.c_size_t, [_i, _i]),
     "s3r_pnp_ransac": (_i, [_vp, _vp, _i, _i64, _i, C.c_double, C.c_double, C.c_double, C.c_double, _f, _i, _i, C.c_uint64,
                             _vp, _vp, _vp, _vp]),

@@ -159,6 +159,11 @@ int s3r_focal_weiszfeld(const float* pts3d, int b, int h, int w, float ppx, floa
   return launch_focal_weiszfeld(pts3d, b, h, w, ppx, ppy, iters, lo, hi, scratch, focal, S(stream));
 }
 
+int s3r_focal_median(const float* pts3d, int b, int h, int w, float ppx, float ppy, float lo, float hi, int32_t* scratch,
+                     float* focal, void* stream) {
+  return launch_focal_median(pts3d, b, h, w, ppx, ppy, lo, hi, scratch, focal, S(stream));
+}
+
 size_t s3r_pnp_workspace_bytes(int b, int n_samples) {
   if (b <= 0 || n_samples <= 0) return 0;
   return pnp_workspace_bytes(b, n_samples);

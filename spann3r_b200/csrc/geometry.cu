@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 
 #include "common.cuh"
+#include "focal_math.cuh"
 
 namespace s3r {
 
@@ -91,6 +92,87 @@ int launch_focal_weiszfeld(const float* pts3d, int B, int H, int W, float ppx, f
     launch_pdl(focal_partial_kernel, dim3(kFocalBlocks, B), dim3(256), 0, st, pts3d, H, W, ppx, ppy, (const float*)focal,
                it == 0 ? 1 : 0, scratch);
     launch_pdl(focal_final_kernel, dim3(B), dim3(256), 0, st, (const float*)scratch, lo, hi, it == iters ? 1 : 0, focal);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// focal_mode='median' (dust3r/post_process.py:26-36): nanmedian over the 2*H*W votes (u z / x, v z / y) of an image.
+// The median is an ELEMENT of the vote set, so it is selected, not averaged: 4 passes of an 8-bit radix select on the
+// order-preserving integer key of the fp32 votes (recomputed on the fly, never materialised); integer histogram
+// atomics only -> bit-exact and deterministic.  Per pass: focal_median_hist_kernel (148 blocks per image, shared-memory
+// histogram of the keys that match the prefix found so far) + focal_median_pick_kernel (one block per image: the bin
+// that holds rank k, the lower median as torch.nanmedian defines it).
+// scratch (int32): per image 256 histogram bins + {prefix, k_lo, k_hi, state}.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMedianBlocks = 148;
+constexpr int kMedianScratch = 256 + 4;
+
+__global__ void __launch_bounds__(256) focal_median_hist_kernel(const float* __restrict__ pts, int H, int W, float ppx,
+                                                                float ppy, int pass, int* __restrict__ scratch) {
+  __shared__ int hist[256];
+  const int b = blockIdx.y;
+  int* sc = scratch + (long long)b * kMedianScratch;
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const long long hw = (long long)H * W, n2 = 2 * hw;
+  const float* p = pts + (long long)b * hw * 3;
+  const int shift = 24 - 8 * pass;
+  const uint32_t prefix = (uint32_t)sc[256];
+  if (sc[259] >= 0) {   // state < 0: no finite-or-infinite vote at all (every vote NaN) -> result NaN, nothing to count
+    for (long long j = blockIdx.x * 256LL + threadIdx.x; j < n2; j += 256LL * kMedianBlocks) {
+      const float f = focal::vote(p, j, hw, W, ppx, ppy);
+      if (f != f) continue;
+      const uint32_t key = focal::order_key(f);
+      if (pass > 0 && (key >> (shift + 8)) != prefix) continue;
+      atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+  }
+  __syncthreads();
+  if (hist[threadIdx.x]) atomicAdd(&sc[threadIdx.x], hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(32) focal_median_pick_kernel(int* __restrict__ scratch, int pass, float lo, float hi,
+                                                               float* __restrict__ focal) {
+  if (threadIdx.x != 0) return;
+  const int b = blockIdx.x;
+  int* sc = scratch + (long long)b * kMedianScratch;
+  if (sc[259] >= 0) {
+    long long k = ((long long)(uint32_t)sc[258] << 32) | (uint32_t)sc[257];
+    if (pass == 0) {
+      long long n = 0;
+      for (int i = 0; i < 256; ++i) n += sc[i];
+      if (n == 0) sc[259] = -1;
+      k = (n - 1) / 2;
+    }
+    if (sc[259] >= 0) {
+      int bin = 0;
+      while (bin < 255 && k >= sc[bin]) k -= sc[bin++];
+      sc[256] = (int)((((uint32_t)sc[256]) << 8) | (uint32_t)bin);
+      sc[257] = (int)(uint32_t)(k & 0xffffffffll);
+      sc[258] = (int)(uint32_t)(k >> 32);
+    }
+  }
+  for (int i = 0; i < 256; ++i) sc[i] = 0;
+  if (pass == 3) {
+    float f = sc[259] >= 0 ? focal::key_value((uint32_t)sc[256]) : nanf("");
+    f = fminf(fmaxf(f, lo), hi);   // focal.clip(min, max): NaN stays NaN (fmaxf / fminf return the non-NaN operand, so
+    if (sc[259] < 0) f = nanf("");  // restore it explicitly)
+    focal[b] = f;
+  }
+}
+
+int launch_focal_median(const float* pts3d, int B, int H, int W, float ppx, float ppy, float lo, float hi, int* scratch,
+                        float* focal, cudaStream_t st) {
+  if (!pts3d || !scratch || !focal || B <= 0 || H <= 0 || W <= 0) {
+    set_error("focal_median: bad arguments");
+    return -1;
+  }
+  cudaMemsetAsync(scratch, 0, sizeof(int) * (size_t)B * kMedianScratch, st);
+  for (int pass = 0; pass < 4; ++pass) {
+    focal_median_hist_kernel<<<dim3(kMedianBlocks, B), 256, 0, st>>>(pts3d, H, W, ppx, ppy, pass, scratch);
+    focal_median_pick_kernel<<<B, 32, 0, st>>>(scratch, pass, lo, hi, focal);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }

@@ -72,6 +72,10 @@ int launch_pnp_ransac(const float* pts3d, const float* img_pts, int B, long long
                       double cx, double cy, float reproj_err, int n_samples, int refine_iters, unsigned long long seed,
                       void* workspace, double* out, unsigned char* inlier_mask, cudaStream_t st);
 
+// focal_mode='median' of the same reference function: exact radix select; scratch = B * 260 int32
+int launch_focal_median(const float* pts3d, int B, int H, int W, float ppx, float ppy, float lo, float hi, int* scratch,
+                        float* focal, cudaStream_t st);
+
 int launch_conf_score(const float* conf, long long n, float* scratch256, float* out, cudaStream_t st);
 
 // fused attention (attention.cu): O = softmax(Q K^T) V per (batch*head), tf32 tcgen05, split-bf16 output

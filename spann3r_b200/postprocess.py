@@ -13,11 +13,11 @@ import torch
 from . import _lib
 
 
-def estimate_focal_knowing_depth(pts3d: torch.Tensor, pp, focal_mode: str = "weiszfeld", min_focal: float = 0.0,
+def estimate_focal_knowing_depth(pts3d: torch.Tensor, pp, focal_mode: str = "median", min_focal: float = 0.0,
                                  max_focal: float = float("inf")) -> torch.Tensor:
     """pts3d [B, H, W, 3] fp32 on the device, pp = (cx, cy) (tensor or pair) -> focal [B] on the device."""
-    if focal_mode != "weiszfeld":
-        raise NotImplementedError("only focal_mode='weiszfeld' (what demo.py uses) is built")
+    if focal_mode not in ("weiszfeld", "median"):
+        raise ValueError(f"bad {focal_mode=}")
     _lib.require_device()
     if not (pts3d.is_cuda and pts3d.dtype == torch.float32 and pts3d.dim() == 4 and pts3d.shape[-1] == 3):
         raise ValueError("expected pts3d [B, H, W, 3] float32 on the GPU")
@@ -27,8 +27,14 @@ def estimate_focal_knowing_depth(pts3d: torch.Tensor, pp, focal_mode: str = "wei
     base = max(H, W) / (2 * math.tan(math.radians(60) / 2))
     lo = min_focal * base
     hi = max_focal * base if math.isfinite(max_focal) else 3.0e38
-    scratch = torch.empty(B * 148 * 2, dtype=torch.float32, device=pts3d.device)
     focal = torch.empty(B, dtype=torch.float32, device=pts3d.device)
+    if focal_mode == "median":      # nanmedian of the per-pixel votes: an exact selection, bit-identical to the reference
+        scratch = torch.empty(B * 260, dtype=torch.int32, device=pts3d.device)
+        _lib.check(_lib.lib().s3r_focal_median(_lib.ptr(pts3d), B, H, W, ppx, ppy, lo,
+                                               max_focal * base if math.isfinite(max_focal) else float("inf"),
+                                               _lib.ptr(scratch), _lib.ptr(focal), _lib.stream_ptr()), "s3r_focal_median")
+        return focal
+    scratch = torch.empty(B * 148 * 2, dtype=torch.float32, device=pts3d.device)
     _lib.check(_lib.lib().s3r_focal_weiszfeld(_lib.ptr(pts3d), B, H, W, ppx, ppy, 10, lo, hi, _lib.ptr(scratch),
                                               _lib.ptr(focal), _lib.stream_ptr()), "s3r_focal_weiszfeld")
     return focal

@@ -32,6 +32,8 @@ if __name__ == "__main__":
         pts = pointmap(seed, B, H, W, f_true)
         pp = torch.tensor((W / 2, H / 2))
         f = estimate_focal_knowing_depth(pts, pp, focal_mode="weiszfeld")
-        cases.append(dict(seed=seed, B=B, H=H, W=W, f_true=f_true, focal=[float(v) for v in f]))
+        fm = estimate_focal_knowing_depth(pts, pp, focal_mode="median")      # an element of the vote set: exact in fp32
+        cases.append(dict(seed=seed, B=B, H=H, W=W, f_true=f_true, focal=[float(v) for v in f],
+                          focal_median=[float(v) for v in fm]))
         print(cases[-1])
     json.dump({"cases": cases}, open(os.path.join(ROOT, "tests", "golden", "focal.json"), "w"), indent=1)
