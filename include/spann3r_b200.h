@@ -16,6 +16,7 @@
 #ifndef SPANN3R_B200_H_
 #define SPANN3R_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -70,6 +70,14 @@ def test_library_exports_every_declared_symbol():
     assert L.s3r_version() == 100
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/spann3r_b200.h is the drop-in boundary: it must compile as C99 on its own (cgo / JNI / ctypes-gen users)."""
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "spann3r_b200.h"\nint (*probe)(void) = s3r_version;\nint main(void) { return probe == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
 def test_rope_table_matches_reference_fallback():
     """engine.rope_cs_table == cos/sin of croco/models/pos_embed.py:120-129 (through the pinned oracle)."""
     from oracle.spann3r_oracle import rope_tables
