@@ -241,3 +241,62 @@ def test_pairwise_and_offline_control_flow_on_a_fake_engine(monkeypatch):
     assert all(v.shape[1:3] == (W, H) for p in preds for v in p.values())
     eng = engines[(1, H, W)]
     assert all(c == ("value", True, False) for c in eng.calls if c[0] == "value")
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every function declared in include/spann3r_b200.h is bound in Python with the same number of arguments and the same
+    scalar kinds (pointer / int / int64 / uint64 / float / double / size_t) -- guards the ctypes layer against ABI drift."""
+    import ctypes as C
+    from spann3r_b200 import _lib, engine  # noqa: F401
+    header = open(os.path.join(ROOT, "include", "spann3r_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"^\s*#.*$", " ", header, flags=re.M)
+    protos = {**_lib._PROTOS, **_lib._EXTRA_PROTOS}
+
+    def kind_c(t):
+        t = t.strip()
+        if "*" in t:
+            return "ptr"
+        t = re.sub(r"\bconst\b", "", t).split()
+        t = " ".join(t[:-1]) if len(t) > 1 else t[0]          # drop the parameter name
+        return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "long long": "i64", "uint64_t": "u64", "float": "f32",
+                "double": "f64", "size_t": "u64", "void": "void", "unsigned": "u32", "uint32_t": "u32"}[t]
+
+    def kind_py(t):
+        if t is None:
+            return "void"
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, (C._Pointer,))):
+            return "ptr"
+        return {C.c_int: "i32", C.c_int64: "i64", C.c_longlong: "i64", C.c_uint64: "u64", C.c_float: "f32",
+                C.c_double: "f64", C.c_size_t: "u64", C.c_uint: "u32"}[t]      # LP64: size_t is uint64
+
+    found = 0
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(s3r_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        assert name in protos, name
+        res, argtypes = protos[name]
+        c_args = [] if args.strip() in ("", "void") else [kind_c(a) for a in args.split(",")]
+        assert len(c_args) == len(argtypes), (name, c_args, argtypes)
+        assert c_args == [kind_py(t) for t in argtypes], (name, c_args, [kind_py(t) for t in argtypes])
+        rk = "ptr" if "*" in ret else kind_c(ret.strip() + " x")
+        assert rk == kind_py(res), (name, rk, res)
+        found += 1
+    assert found == len(protos), (found, len(protos))
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_device():
+    """Argument validation of the C ABI happens before any CUDA call: status < 0 (or NULL / 0) plus a message from
+    s3r_last_error(), no exception, no crash -- checked here without a GPU."""
+    import ctypes as C
+    from spann3r_b200 import _lib, engine
+    L = _lib.lib()
+    assert L.s3r_pnp_workspace_bytes(0, 100) == 0 and L.s3r_pnp_workspace_bytes(2, 100) > 2 * 400 * 96
+    assert L.s3r_pnp_ransac(None, None, 1, 100, 10, 1.0, 1.0, 0.0, 0.0, 8.0, 100, 15, 0, None, None, None, None) == -1
+    assert b"pnp_ransac" in L.s3r_last_error()
+    assert L.s3r_focal_median(None, 1, 8, 8, 4.0, 4.0, 0.0, 1.0, None, None, None) == -1
+    assert L.s3r_focal_weiszfeld(None, 0, 8, 8, 4.0, 4.0, 10, 0.0, 1.0, None, None, None) == -1
+    assert not L.s3r_engine_create(None, 1, 224, 224, 2)
+    w = engine.ModelW()
+    assert not L.s3r_engine_create(C.byref(w), 1, 100, 224, 2)            # height not a multiple of 16
+    assert b"multiples of 16" in L.s3r_last_error()
+    assert not L.s3r_engine_create(C.byref(w), 0, 224, 224, 2)
