@@ -37,7 +37,14 @@ def _newer(src_list, target) -> bool:
     return any(os.path.getmtime(s) > t for s in src_list)
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, defines=(), lib: str = LIB, obj_dir: str = OBJ) -> str:
+    """defines / lib / obj_dir: build an A/B variant next to the shipped library, e.g.
+    `python -m spann3r_b200.build --variant attn56 -DS3R_ATTN_PRODUCER_REGS=56` -> ab/libspann3r_b200_attn56.so (git-ignored,
+    travels with gpurun; select it with S3R_LIB=...).  The default build takes no defines."""
+    return _build(force, verbose, tuple(defines), lib, obj_dir)
+
+
+def _build(force, verbose, defines, LIB, OBJ) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(HERE), "include", "spann3r_b200.h")]
     if not force and not _newer(srcs + hdrs, LIB):
@@ -48,7 +55,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if force or _newer([src] + hdrs, obj):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + list(defines) + ["-c", src, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -68,4 +75,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--variant" in sys.argv:
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        root = os.path.dirname(HERE)
+        os.makedirs(os.path.join(root, "ab"), exist_ok=True)
+        print(build(force=True, defines=[a for a in sys.argv if a.startswith("-D")],
+                    lib=os.path.join(root, "ab", f"libspann3r_b200_{name}.so"), obj_dir=os.path.join(root, "ab", f"obj_{name}")))
+    else:
+        build(force="--force" in sys.argv)

@@ -17,6 +17,12 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef S3R_ATTN_PRODUCER_REGS
+#define S3R_ATTN_PRODUCER_REGS 40
+#endif
+static_assert(S3R_ATTN_PRODUCER_REGS % 8 == 0 && S3R_ATTN_PRODUCER_REGS >= 24 && S3R_ATTN_PRODUCER_REGS <= 64,
+              "setmaxnreg takes a multiple of 8; 128 x R + 256 x 224 registers must fit the 64 K file");
+
 namespace s3r {
 
 namespace attn {
@@ -121,7 +127,9 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
 
   // register re-balancing: the TMA / MMA warpgroup needs few registers, each softmax thread holds a 128-key row
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  // S3R_ATTN_PRODUCER_REGS (build-time, default 40 = the verified build): registers left to this warpgroup; 128 x R + 256 x 224
+  // must fit the 64 K register file (R <= 64).  profiles/r1_ptxas_resources.md: the pair-tile variant spills ~0.2 KB at 40.
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S3R_ATTN_PRODUCER_REGS));
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, Cfg<PAIR>::QB);
