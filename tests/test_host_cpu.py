@@ -300,3 +300,20 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
     assert not L.s3r_engine_create(C.byref(w), 1, 100, 224, 2)            # height not a multiple of 16
     assert b"multiples of 16" in L.s3r_last_error()
     assert not L.s3r_engine_create(C.byref(w), 0, 224, 224, 2)
+
+
+def test_only_checkers_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing in the product package or in tools/ may import it; bench.py may, in its
+    baseline legs only (run_reference, cpu_baseline, reference_eager_gpu), and __graft_entry__.smoke() as the checker."""
+    import glob
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    for path in glob.glob(os.path.join(ROOT, "spann3r_b200", "**", "*.py"), recursive=True) + glob.glob(os.path.join(ROOT, "tools", "*.py")):
+        assert not pat.search(open(path).read()), f"{path} imports the oracle"
+    for path in glob.glob(os.path.join(ROOT, "spann3r_b200", "csrc", "*")):
+        assert "oracle" not in open(path).read(), path
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    timed = bench[bench.index("# ---- timed: inputs resident in HBM"): bench.index("# ---- roofline leg")]
+    assert "oracle" not in timed and "orc." not in timed           # never inside the measured regions
+    assert len(pat.findall(bench)) == 3
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert pat.search(entry[entry.index("def smoke"):]) and not pat.search(entry[: entry.index("def smoke")])
