@@ -3,7 +3,9 @@
 # not eat the call.  Usage (from the repo root, through gpurun):
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r2 tests bench ab ncu'
 # steps: tests = full `pytest -m gpu` (+ durations), bench = bench.py (N=1), ab = tools/ab_overlap.py,
-#        ncu = launch list of one sequence (+ DRAM bytes) summarised by tools/summarize_ncu.py, demo = tools/bench_demo_path.py
+#        ncu = launch list of one sequence (+ DRAM bytes) summarised by tools/summarize_ncu.py, demo = tools/bench_demo_path.py,
+#        unverified = the tests marked gpu_unverified (kernels written without a GPU), sanitize = compute-sanitizer memcheck /
+#        racecheck / synccheck over the op-level tests (slow: minutes per tool)
 # Outputs: gpurun_out/<tag>_*.  Copy what should be judged into profiles/ afterwards.  Round-1 timings for budgeting: the
 # 11 golden / portrait / PnP tests 147 s, bench.py 60-70 s (incl. the eager-GPU and CPU-baseline legs), bench_demo_path 40 s,
 # first `import torch` on a fresh box up to 60 s, ncu launch list of one sequence ~3 min.
@@ -19,6 +21,13 @@ for step in "$@"; do
              --profile-from-start off --csv --log-file gpurun_out/${tag}_launches.csv python tools/profile_seq.py > gpurun_out/${tag}_ncu.log 2>&1
            python tools/summarize_ncu.py gpurun_out/${tag}_launches.csv --title "${tag}: ncu launch list of ONE 10-frame 512x384 sequence (B=1)" \
              > gpurun_out/${tag}_launches.md 2>> gpurun_out/${tag}_ncu.log; head -20 gpurun_out/${tag}_launches.md ;;
+    sanitize) # memcheck + racecheck + synccheck on the small op-level tests (tcgen05 / TMA / mbarrier kernels) and one 224x224 sequence
+           for tool in memcheck racecheck synccheck; do
+             timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_ops_gpu.py tests/test_pnp.py -q -m gpu -x -k "not 7680" \
+               > gpurun_out/${tag}_sanitizer_${tool}.log 2>&1; echo "$tool exit $?" | tee -a gpurun_out/${tag}_sanitizer_${tool}.log
+             grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/${tag}_sanitizer_${tool}.log | tail -3
+           done ;;
+    unverified) timeout 300 python -m pytest tests -q -m gpu_unverified > gpurun_out/${tag}_unverified.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_unverified.log; tail -8 gpurun_out/${tag}_unverified.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
