@@ -415,11 +415,17 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
     two = 1;
     bn = (g2_mode == 256 && N % 256 == 0) ? 256 : 128;
   }
+  // EXPERIMENT (off by default, not yet measured): where the planner settles on 1-CTA 128 x 64 tiles -- the N = 768 / 1024
+  // GEMMs of the decoder and value encoder at B = 1, one wave of 144 CTAs, bound by the per-SM operand ingest (DESIGN.md
+  // section 4b) -- a 256 x 64 CTA-pair tile keeps the CTA count and the MMA work per SM but stages only half of B per SM:
+  // 40 KB instead of 48 KB per k-block.  S3R_GEMM2_64=1 switches those launches over for an in-situ A/B.
+  static const bool pair64 = getenv("S3R_GEMM2_64") && atoi(getenv("S3R_GEMM2_64")) != 0;
+  if (pair64 && force_bn == 0 && !two && bn == 64 && m_tiles_group % 2 == 0 && N >= 64) two = 1;
   if (force_bn == 1128) { two = legal2 ? 1 : 0; bn = 128; }   // width 128 (EPI_HEADTAIL), CTA pairs where legal
   else if (force_bn >= 2000) { two = 1; bn = force_bn - 2000; }
   else if (force_bn > 0) { two = 0; bn = force_bn; }
-  if (two && (m_tiles_group % 2 != 0 || (bn != 128 && bn != 256))) {
-    set_error("gemm_plan_init: 2-CTA tiles need an even m-tile count per group and bn in {128,256}");
+  if (two && (m_tiles_group % 2 != 0 || (bn != 64 && bn != 128 && bn != 256))) {
+    set_error("gemm_plan_init: 2-CTA tiles need an even m-tile count per group and bn in {64,128,256}");
     return -1;
   }
   plan->two_cta = two;

@@ -399,6 +399,7 @@ static int launch2_epi(const GemmPlan& plan, cudaStream_t stream) {
 
 int gemm2_launch(const GemmPlan& plan, cudaStream_t stream) {
   switch (plan.bn) {
+    case 64: return launch2_epi<64>(plan, stream);   // experiment (S3R_GEMM2_64=1 / force_bn 2064): 256 x 64 pair tiles
     case 128: return launch2_epi<128>(plan, stream);
     case 256: return launch2_epi<256>(plan, stream);
   }

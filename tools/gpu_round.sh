@@ -4,6 +4,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r2 tests bench ab ncu'
 # steps: tests = full `pytest -m gpu` (+ durations), bench = bench.py (N=1), ab = tools/ab_overlap.py,
 #        ncu = launch list of one sequence (+ DRAM bytes) summarised by tools/summarize_ncu.py, demo = tools/bench_demo_path.py,
+#        ab64 = bench.py with S3R_GEMM2_64=0/1/0 (256 x 64 CTA-pair tiles where the planner picks 1-CTA 128 x 64),
 #        unverified = the tests marked gpu_unverified (kernels written without a GPU), sanitize = compute-sanitizer memcheck /
 #        racecheck / synccheck over the op-level tests (slow: minutes per tool)
 # Outputs: gpurun_out/<tag>_*.  Copy what should be judged into profiles/ afterwards.  Round-1 timings for budgeting: the
@@ -16,6 +17,10 @@ for step in "$@"; do
     tests) timeout 900 python -m pytest tests -q -m gpu -x --durations=15 > gpurun_out/${tag}_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_tests.log; tail -25 gpurun_out/${tag}_tests.log ;;
     bench) timeout 240 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-900 gpurun_out/${tag}_bench.json ;;
     ab)    timeout 240 python tools/ab_overlap.py > gpurun_out/${tag}_ab_overlap.json 2> gpurun_out/${tag}_ab_overlap.err; tail -3 gpurun_out/${tag}_ab_overlap.err; cat gpurun_out/${tag}_ab_overlap.json ;;
+    ab64)  # in-situ A/B of the 256 x 64 pair-tile experiment (env read once per process): default, variant, default again
+           for v in 0 1 0; do S3R_GEMM2_64=$v timeout 200 python bench.py --steps 8 --warmup 3 --no-eager-gpu --no-cpu-baseline 2>/dev/null \
+             | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('S3R_GEMM2_64=$v', round(d['value'],1), 'frames/s', round(d['ms_per_step'],2), 'ms  gemm', round(d['roofline']['gemm_ms_per_seq'],2), 'ms')" \
+             | tee -a gpurun_out/${tag}_ab64.txt; done ;;
     demo)  timeout 200 python tools/bench_demo_path.py > gpurun_out/${tag}_bench_demo_path.json 2> gpurun_out/${tag}_demo.err; tail -3 gpurun_out/${tag}_demo.err; cat gpurun_out/${tag}_bench_demo_path.json ;;
     ncu)   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
              --profile-from-start off --csv --log-file gpurun_out/${tag}_launches.csv python tools/profile_seq.py > gpurun_out/${tag}_ncu.log 2>&1
