@@ -130,6 +130,9 @@ def main():
                     help="skip the `reference_eager_gpu` leg: the reference ALGORITHM as PyTorch eager on this GPU (the oracle "
                          "port with the reference's TF32 default, and in strict fp32) -- the peer the north star asks to be "
                          "reported beside the CUDA path in the same run.  Untimed for the headline; ~5 s")
+    ap.add_argument("--raw-checkpoint", action="store_true",
+                    help="random-init weights as constructed (SURVEY.md §8d: ill-conditioned memory reads from the 7th frame on) "
+                         "instead of the sharpened checkpoint the headline is quoted on; the work per frame is identical")
     ap.add_argument("--batch", type=int, default=1,
                     help="sequences advanced in lockstep per GPU (BASELINE config[2] runs 8 per GPU); the headline is 1")
     args = ap.parse_args()
@@ -147,7 +150,7 @@ def main():
     W_ = max(args.warmup, 3)
     K = max(args.steps, 1)
     F_ = args.frames
-    sd = synth.make_state_dict(sharpen=True)
+    sd = synth.make_state_dict(sharpen=not args.raw_checkpoint)
     model = Spann3R(dus3r_name=None)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval()
@@ -298,7 +301,7 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; tf32 attention)", "data": "synthetic",
             "config": {"workload": f"{F_}-frame {WIDTH}x{HEIGHT} sequence per step, batch {BATCH} per GPU, ViT-L enc / ViT-B dec + DPT, "
-                                   "random-init sharpened checkpoint (SURVEY.md §8d config 2)",
+                                   f"random-init {'raw' if args.raw_checkpoint else 'sharpened'} checkpoint (SURVEY.md §8d config 2)",
                        "parallelism": f"{world} independent replicas (one sequence stream per GPU, no collective)",
                        "l2": "per-step working set (2.6 GB packed weights + activations) >> 126 MB L2; inputs alternate between "
                              "2 distinct sequences"},
