@@ -93,6 +93,9 @@ class AsymmetricCroCo3DStereo(ParamModule):
     def _decoder(self, f1, pos1, f2, pos2):
         """dust3r/model.py:186-205 -> (dec1, dec2), 13 tensors each ([f_enc, d1..d12], d12 normed)."""
         o = self._owner
+        if o._hw is None or (o._hw[0] // 16) * (o._hw[1] // 16) != f1.shape[1]:
+            raise RuntimeError("_decoder needs the image size of the features it is given: call _encode_image (or the "
+                               "model) on that resolution first -- the token count alone does not determine (H, W)")
         eng = o._engine_for(f1.shape[0], o._hw[0], o._hw[1])
         dec_all = eng.decode(f1.contiguous(), f2.contiguous(), want_all=True)
         dec1 = [f1] + [dec_all[l, 0] for l in range(12)]
