@@ -124,8 +124,17 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """Current stream OF THE GIVEN DEVICE (default: the current device).  Callers that take tensors pass the tensor's
+    device and run under `on_device(...)`: the library allocates, configures and launches on the CURRENT device."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(t_or_dev):
+    """Context manager: make the tensor's (or given) CUDA device current for the duration of a library call, so that
+    `Spann3R(...).to('cuda:1')` works without a global `torch.cuda.set_device(1)` (as the reference's `.to(device)` does)."""
+    dev = t_or_dev.device if isinstance(t_or_dev, torch.Tensor) else torch.device(t_or_dev)
+    return torch.cuda.device(dev)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -138,7 +147,8 @@ def split(x: torch.Tensor, relu: bool = False):
     rows = x.numel() // c
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     lo = torch.empty_like(hi)
-    check(lib().s3r_split(ptr(x), c, ptr(hi), ptr(lo), c, 0, rows, c, int(relu), stream_ptr()), "s3r_split")
+    with on_device(x):
+        check(lib().s3r_split(ptr(x), c, ptr(hi), ptr(lo), c, 0, rows, c, int(relu), stream_ptr(x.device)), "s3r_split")
     return hi, lo
 
 
@@ -149,13 +159,18 @@ def layernorm(x, w, b, eps, want_f32=True, want_planes=False):
     out = torch.empty_like(x) if want_f32 else None
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_planes else None
     lo = torch.empty_like(hi) if want_planes else None
-    check(lib().s3r_layernorm(ptr(x), c, ptr(w), ptr(b), 0, 0, float(eps), rows, c, ptr(out), c, ptr(hi), ptr(lo), c, 0,
-                              0, stream_ptr()), "s3r_layernorm")
+    with on_device(x):
+        check(lib().s3r_layernorm(ptr(x), c, ptr(w), ptr(b), 0, 0, float(eps), rows, c, ptr(out), c, ptr(hi), ptr(lo), c, 0,
+                                  0, stream_ptr(x.device)), "s3r_layernorm")
     return out, hi, lo
 
 
-def gemm(desc: GemmDesc):
-    check(lib().s3r_gemm(C.byref(desc), stream_ptr()), "s3r_gemm")
+def gemm(desc: GemmDesc, device=None):
+    """device: the device the descriptor's pointers live on (default: the current device)."""
+    if device is None:
+        return check(lib().s3r_gemm(C.byref(desc), stream_ptr()), "s3r_gemm")
+    with on_device(device):
+        check(lib().s3r_gemm(C.byref(desc), stream_ptr(device)), "s3r_gemm")
 
 
 def linear(x_planes, w_planes, bias=None, act=ACT_NONE, res=None, want_f32=True, want_planes=False, plane_relu=False,
@@ -181,7 +196,7 @@ def linear(x_planes, w_planes, bias=None, act=ACT_NONE, res=None, want_f32=True,
         d.out_f32, d.ldo = out.data_ptr(), N
     if oh is not None:
         d.out_hi, d.out_lo, d.ldp = oh.data_ptr(), ol.data_ptr(), N
-    gemm(d)
+    gemm(d, dev)
     return out, oh, ol
 
 
@@ -190,5 +205,6 @@ def conf_score(conf: torch.Tensor) -> torch.Tensor:
     assert conf.is_cuda and conf.dtype == torch.float32 and conf.is_contiguous()
     scratch = torch.empty(256, dtype=torch.float32, device=conf.device)
     out = torch.empty(1, dtype=torch.float32, device=conf.device)
-    check(lib().s3r_conf_score(ptr(conf), conf.numel(), ptr(scratch), ptr(out), stream_ptr()), "s3r_conf_score")
+    with on_device(conf):
+        check(lib().s3r_conf_score(ptr(conf), conf.numel(), ptr(scratch), ptr(out), stream_ptr(conf.device)), "s3r_conf_score")
     return out

@@ -433,7 +433,8 @@ int attn_plan_init(AttnPlan* plan, const float* q, const float* k, const float* 
 template <bool PAIR>
 static int attn_launch_t(const AttnPlan& plan, const AttnArgs& a, cudaStream_t st) {
   using namespace attn;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
+  bool& attr_set = once.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM);
     if (e != cudaSuccess) {

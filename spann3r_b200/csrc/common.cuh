@@ -272,6 +272,17 @@ __device__ __forceinline__ void st_f4(float* p, float a, float b, float c, float
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
+// host: "configured once" flags.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute, so a
+// process that drives several GPUs (Spann3R(...).to('cuda:1') beside one on cuda:0) needs one flag per device ordinal.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return done[d & 63];
+  }
+};
+
 // host: launch with the PDL attribute
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

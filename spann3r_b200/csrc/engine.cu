@@ -61,7 +61,13 @@ struct PlanCache {
   std::vector<AttnPlan> attns;
   size_t gc = 0, ac = 0;
   bool building = true;
-  void begin() { gc = ac = 0; }
+  void begin() {
+    gc = ac = 0;
+    if (building) {   // a previous first pass failed half way (e.g. a plan_init error): start the plan list over
+      gemms.clear();
+      attns.clear();
+    }
+  }
   void end() { building = false; }
 };
 
@@ -70,6 +76,7 @@ struct PlanCache {
 struct s3r_engine {
   s3r_model_w w;
   int B, H, W, gh, gw, N, Npad, max_images;
+  int device = 0;   // ordinal the workspace lives on; every stage call must be made with this device current
   std::vector<void*> allocs;
   double flops = 0;
   long long launches = 0;
@@ -125,6 +132,15 @@ struct s3r_engine {
     }
     allocs.push_back(p);
     return reinterpret_cast<T*>(p);
+  }
+  void release(void* p) {   // cudaFree (synchronising) + forget; null is fine
+    if (!p) return;
+    for (size_t i = 0; i < allocs.size(); ++i)
+      if (allocs[i] == p) {
+        cudaFree(p);
+        allocs.erase(allocs.begin() + i);
+        return;
+      }
   }
   Planes alloc_planes(size_t n) {
     Planes p;
@@ -245,6 +261,19 @@ struct s3r_engine {
 };
 
 // ------------------------------------------------------------------------------------------------
+// The library launches on the CURRENT device (stream, cudaFuncSetAttribute and tensor maps are per device): a stage call
+// made while another device is current would run on the wrong GPU with this engine's pointers.  Refuse it.
+static int engine_device_ok(const s3r_engine* e, const char* what) {
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur == e->device) return 0;
+  set_error("%s: the engine lives on device %d but device %d is current (wrap the call in torch.cuda.device(...))", what,
+            e->device, cur);
+  return -1;
+}
+#define S3R_ENGINE_DEVICE(e, what) \
+  do { if (int r_ = engine_device_ok((e), (what))) return r_; } while (0)
+
 static __global__ void fill_pos_kernel(int* pos, long long rows, int N, int gw) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -271,6 +300,7 @@ s3r_engine* s3r_engine_create(const s3r_model_w* w, int batch, int height, int w
   }
   if (max_images < 2 * batch) max_images = 2 * batch;
   s3r_engine* e = new s3r_engine();
+  cudaGetDevice(&e->device);
   e->w = *w;
   e->B = batch; e->H = height; e->W = width;
   e->gh = height / 16; e->gw = width / 16;
@@ -449,6 +479,7 @@ long long s3r_engine_take_launches(s3r_engine* e) {
 // ------------------------------------------------------------------------------------------------
 int s3r_engine_encode(s3r_engine* e, const float* img, int nimg, float* feat, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_encode");
   if (nimg <= 0 || nimg > e->max_images) {
     set_error("s3r_engine_encode: nimg=%d outside [1, %d]", nimg, e->max_images);
     return -1;
@@ -479,6 +510,7 @@ int s3r_engine_encode(s3r_engine* e, const float* img, int nimg, float* feat, vo
 // ------------------------------------------------------------------------------------------------
 int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* dec_all, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_decode");
   PlanCache& pc = e->pc_decode;
   pc.begin();
   const int N = e->N, B = e->B;
@@ -577,6 +609,7 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
 // ------------------------------------------------------------------------------------------------
 int s3r_engine_keyheads(s3r_engine* e, const float* feat1, const float* feat2, float* k1, float* k2, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_keyheads");
   PlanCache& pc = e->pc_keys;
   pc.begin();
   const long long R = (long long)e->B * e->N;
@@ -609,6 +642,7 @@ int s3r_engine_keyheads(s3r_engine* e, const float* feat1, const float* feat2, f
 // ------------------------------------------------------------------------------------------------
 int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_heads");
   PlanCache& pc = e->pc_heads;
   pc.begin();
   const s3r_dpt_w& d = e->w.dpt;
@@ -716,6 +750,7 @@ int s3r_engine_heads(s3r_engine* e, float* pts, float* conf, void* stream) {
 // ------------------------------------------------------------------------------------------------
 int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, int flags, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_value");
   if (flags & ~(S3R_VALUE_PTS_TRANSPOSED | S3R_VALUE_ROPE)) {
     set_error("s3r_engine_value: unknown flags 0x%x", flags);
     return -1;
@@ -761,18 +796,23 @@ int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, in
 int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float* out,
                            void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_memory_read");
   const int B = e->B, N = e->N, M = bank->len, cap = bank->cap;
   if (M <= 0 || M > cap || cap % 8 != 0) {
     set_error("s3r_engine_memory_read: bad bank (len=%d cap=%d; cap must be a multiple of 8)", M, cap);
     return -1;
   }
   if (cap > e->mem_cap) {  // (re)size the score / probability scratch for this bank capacity (rare)
-    e->Sm = e->alloc<float>((size_t)B * N * cap);
+    e->release(e->Sm); e->release(e->Pm.hi); e->release(e->Pm.lo);   // the old scratch is dead: no stage is in flight on it
+    e->Sm = e->alloc<float>((size_t)B * N * cap);                    // that a later launch of this stream could overtake
     e->Pm = e->alloc_planes((size_t)B * N * cap);
     if (e->status) return e->status;
     e->mem_cap = cap;
     e->pc_memread.clear();
   }
+  // plans bake in (len, cap, bank pointers): a process that keeps creating banks at new addresses must not grow the
+  // cache without bound (one sequence touches <= 16 distinct lengths)
+  if (e->pc_memread.size() > 256) e->pc_memread.clear();
   PlanCache& pc = e->pc_memread[std::make_tuple((long long)M, (long long)cap, (const void*)bank->kn_hi, (const void*)bank->kn_lo,
                                                 (const void*)bank->vnt_hi, (const void*)bank->vnt_lo)];
   pc.begin();
@@ -808,6 +848,7 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
 int s3r_engine_memory_append(s3r_engine* e, const s3r_bank* bank, const float* feat_k, const float* feat_v,
                              void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_memory_append");
   const int B = e->B, N = e->N, M = bank->len, cap = bank->cap;
   if (M + N > cap) {
     set_error("s3r_engine_memory_append: bank full (len=%d + %d > cap=%d)", M, N, cap);
@@ -837,6 +878,7 @@ int s3r_engine_memory_append(s3r_engine* e, const s3r_bank* bank, const float* f
 
 int s3r_engine_check_sim(s3r_engine* e, const s3r_bank* bank, const float* feat_k, int wm, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  S3R_ENGINE_DEVICE(e, "s3r_engine_check_sim");
   const int B = e->B, N = e->N;
   if (wm <= 0 || wm > 8 || wm * N > bank->len) {
     set_error("s3r_engine_check_sim: wm=%d invalid for bank len %d", wm, bank->len);

@@ -356,15 +356,16 @@ static int next_pow2(int x) {
   return p;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+static int g_num_sms[64] = {};   // per device ordinal
+int num_sms() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = g_num_sms[dev & 63];
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return g_num_sms;
+  return n;
 }
 
 int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo,
@@ -466,7 +467,8 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
 template <int BN, int EPI>
 static int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
+  bool& attr_set = once.cur();
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);

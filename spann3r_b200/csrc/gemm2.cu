@@ -350,7 +350,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
 template <int BN, int EPI>
 static int launch2_bn(const GemmPlan& plan, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
+  bool& attr_set = once.cur();
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(gemm2_bf16x3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);

@@ -87,10 +87,10 @@ int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int
     set_error("mem_softmax: bank of %d tokens exceeds the 51200-token row buffer", M);
     return -1;
   }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDeviceOnce once;
+  if (smem > 48 * 1024 && !once.cur()) {
     cudaFuncSetAttribute(mem_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = 200 * 1024;
+    once.cur() = true;
   }
   launch_pdl(mem_softmax_kernel, dim3((unsigned)rows), dim3(256), smem, st, S, ldS, M, Mpad, scale, thresh, phi, plo, ldP);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;

@@ -89,10 +89,10 @@ int launch_resample_h_u8(const uint8_t* src, long long row_stride, int rows, int
     set_error("resample_h: source span of %d pixels per 128 output columns is too large", max_span);
     return -1;
   }
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDeviceOnce once;
+  if (smem > 48 * 1024 && !once.cur()) {
     cudaFuncSetAttribute(resample_h_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    configured = 160 * 1024;
+    once.cur() = true;
   }
   launch_pdl(resample_h_u8_kernel, dim3((out_cols + 127) / 128, rows), dim3(128), smem, st, src, row_stride, out_cols, bounds,
              kk, ksize, dst);

@@ -111,6 +111,15 @@ def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: 
     return (w64 * gamma.double()[None, :]).float(), (b64 + w64 @ beta.double()).float()
 
 
+def split_bf16_host_rowsum(w: torch.Tensor) -> torch.Tensor:
+    """Row sums of hi + lo where hi = bf16(w), lo = bf16(w - hi): the same round-to-nearest-even split the device kernel
+    (`s3r_split`) makes, evaluated on the host in fp64 -- the column-sum vector `cs` of a LayerNorm-folded Linear must be the
+    sum of what the tensor core actually multiplies (tests/test_ops_gpu.py checks host == device planes)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return (hi.double() + lo.double()).sum(dim=1).float()
+
+
 class PackedWeights:
     """Device-resident packed weights + the `s3r_model_w` pointer table."""
 
@@ -126,19 +135,21 @@ class PackedWeights:
         torch.cuda.synchronize(self.device)
 
     # -- helpers ---------------------------------------------------------------------------------
+    # All one-time layout work (stacking groups, permutes, LayerNorm folding, column sums) is host arithmetic on the
+    # CPU copy of the checkpoint; the device sees one upload per tensor and the library's own split kernel.  (Round 1 did
+    # this with fp64 torch ops on the GPU: ~900 library launches before the first tensor-core kernel.)
     def _t(self, key):
-        return self.sd[key].detach().to(self.device, torch.float32)
+        return self.sd[key].detach().to("cpu", torch.float32)
 
     def _f32(self, t: torch.Tensor):
-        t = t.contiguous()
+        t = t.contiguous().to(self.device)
         self._keep.append(t)
         self.param_bytes += t.numel() * 4
         return t.data_ptr()
 
     def _planes(self, w2d: torch.Tensor) -> Planes:
-        hi, lo = _lib.split(w2d.contiguous())
+        hi, lo = _lib.split(w2d.contiguous().to(self.device))
         self._keep += [hi, lo]
-        self._last_planes = (hi, lo)
         self.param_bytes += hi.numel() * 4
         p = Planes()
         p.hi, p.lo = hi.data_ptr(), lo.data_ptr()
@@ -171,8 +182,7 @@ class PackedWeights:
             ws.append(wf)
             bs.append(bf)
         l = self._lin(ws, bs)
-        hi, lo = self._last_planes
-        l.cs = self._f32((hi.double() + lo.double()).sum(dim=1).float())
+        l.cs = self._f32(torch.cat([split_bf16_host_rowsum(w.reshape(w.shape[0], -1)) for w in ws], dim=0))
         return l
 
     def _conv3(self, names, bias=True) -> Lin:   # [Cout, Cin, 3, 3] -> [Cout, tap, Cin]
@@ -252,7 +262,7 @@ class PackedWeights:
         s.value_norm = self._ln(["value_norm"])
         s.value_out = self._linear(["value_out"])
         s.norm_q, s.norm_k, s.norm_v = self._ln(["norm_q"]), self._ln(["norm_k"]), self._ln(["norm_v"])
-        s.rope_cs = self._f32(rope_cs_table().to(self.device))
+        s.rope_cs = self._f32(rope_cs_table())
         s.rope_maxpos = ROPE_MAXPOS
 
 
@@ -302,9 +312,16 @@ class Engine:
         self.max_images = max(max_images, 2 * batch)
         self.device = weights.device
         L = _lib.lib()
-        self._h = L.s3r_engine_create(C.byref(weights.struct), batch, height, width, self.max_images)
+        with torch.cuda.device(self.device):     # the engine allocates its workspace on the CURRENT device
+            self._h = L.s3r_engine_create(C.byref(weights.struct), batch, height, width, self.max_images)
         if not self._h:
             raise _lib.S3RError("s3r_engine_create failed: " + L.s3r_last_error().decode())
+
+    def _call(self, name, what, *args):
+        """One engine stage on the engine's own device and that device's current stream (the library launches on the
+        current device; the C side refuses a call made while another device is current)."""
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(_lib.lib(), name)(self._h, *args, _lib.stream_ptr(self.device)), what)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -328,27 +345,25 @@ class Engine:
         nimg = img.shape[0]
         self._chk(img, (nimg, 3, self.H, self.W))
         feat = self._new(nimg, self.N, 1024)
-        _lib.check(_lib.lib().s3r_engine_encode(self._h, _lib.ptr(img), nimg, _lib.ptr(feat), _lib.stream_ptr()), "encode")
+        self._call("s3r_engine_encode", "encode", _lib.ptr(img), nimg, _lib.ptr(feat))
         return feat
 
     def decode(self, f1, f2, want_all=False):
         self._chk(f1, (self.B, self.N, 1024)); self._chk(f2, (self.B, self.N, 1024))
         dec_all = self._new(12, 2, self.B, self.N, 768) if want_all else None
-        _lib.check(_lib.lib().s3r_engine_decode(self._h, _lib.ptr(f1), _lib.ptr(f2), _lib.ptr(dec_all), _lib.stream_ptr()),
-                   "decode")
+        self._call("s3r_engine_decode", "decode", _lib.ptr(f1), _lib.ptr(f2), _lib.ptr(dec_all))
         return dec_all
 
     def keyheads(self, feat1, feat2):
         self._chk(feat1, (self.B, self.N, 1024)); self._chk(feat2, (self.B, self.N, 1024))
         k1, k2 = self._new(self.B, self.N, 1024), self._new(self.B, self.N, 1024)
-        _lib.check(_lib.lib().s3r_engine_keyheads(self._h, _lib.ptr(feat1), _lib.ptr(feat2), _lib.ptr(k1), _lib.ptr(k2),
-                                                  _lib.stream_ptr()), "keyheads")
+        self._call("s3r_engine_keyheads", "keyheads", _lib.ptr(feat1), _lib.ptr(feat2), _lib.ptr(k1), _lib.ptr(k2))
         return k1, k2
 
     def heads(self):
         pts = self._new(2, self.B, self.H, self.W, 3)
         conf = self._new(2, self.B, self.H, self.W)
-        _lib.check(_lib.lib().s3r_engine_heads(self._h, _lib.ptr(pts), _lib.ptr(conf), _lib.stream_ptr()), "heads")
+        self._call("s3r_engine_heads", "heads", _lib.ptr(pts), _lib.ptr(conf))
         return pts, conf
 
     def value(self, pts3d, feat_k1, transposed: bool = False, rope: bool = False):
@@ -357,48 +372,49 @@ class Engine:
         self._chk(pts3d, (self.B, self.H, self.W, 3)); self._chk(feat_k1, (self.B, self.N, 1024))
         out = self._new(self.B, self.N, 1024)
         flags = (VALUE_PTS_TRANSPOSED if transposed else 0) | (VALUE_ROPE if rope else 0)
-        _lib.check(_lib.lib().s3r_engine_value(self._h, _lib.ptr(pts3d), _lib.ptr(feat_k1), flags, _lib.ptr(out),
-                                               _lib.stream_ptr()), "value")
+        self._call("s3r_engine_value", "value", _lib.ptr(pts3d), _lib.ptr(feat_k1), flags, _lib.ptr(out))
         return out
 
     def memory_read(self, bank: MemoryBank, feat, thresh: float):
         self._chk(feat, (self.B, self.N, 1024))
         out = self._new(self.B, self.N, 1024)
         bs = bank.struct()
-        _lib.check(_lib.lib().s3r_engine_memory_read(self._h, C.byref(bs), _lib.ptr(feat), float(thresh), _lib.ptr(out),
-                                                     _lib.stream_ptr()), "memory_read")
+        self._call("s3r_engine_memory_read", "memory_read", C.byref(bs), _lib.ptr(feat), float(thresh), _lib.ptr(out))
         return out
 
     def memory_append(self, bank: MemoryBank, feat_k, feat_v):
         self._chk(feat_k, (self.B, self.N, 1024)); self._chk(feat_v, (self.B, self.N, 1024))
         bs = bank.struct()
-        _lib.check(_lib.lib().s3r_engine_memory_append(self._h, C.byref(bs), _lib.ptr(feat_k), _lib.ptr(feat_v),
-                                                       _lib.stream_ptr()), "memory_append")
+        self._call("s3r_engine_memory_append", "memory_append", C.byref(bs), _lib.ptr(feat_k), _lib.ptr(feat_v))
         bank.len += self.N
 
     def check_sim(self, bank: MemoryBank, feat_k, wm: int) -> torch.Tensor:
         out = self._new(self.B, wm)
         bs = bank.struct()
-        _lib.check(_lib.lib().s3r_engine_check_sim(self._h, C.byref(bs), _lib.ptr(feat_k), wm, _lib.ptr(out),
-                                                   _lib.stream_ptr()), "check_sim")
+        self._call("s3r_engine_check_sim", "check_sim", C.byref(bs), _lib.ptr(feat_k), wm, _lib.ptr(out))
         return out
 
     def take_flops(self) -> float:
         return float(_lib.lib().s3r_engine_take_flops(self._h))
+
+    def _on(self):
+        return torch.cuda.device(self.device)
 
     def profile(self, on: bool):
         _lib.lib().s3r_engine_profile(self._h, int(on))
 
     def profile_read(self) -> dict:
         out = (C.c_double * 6)()
-        _lib.check(_lib.lib().s3r_engine_profile_read(self._h, out), "profile_read")
+        with self._on():
+            _lib.check(_lib.lib().s3r_engine_profile_read(self._h, out), "profile_read")
         return dict(gemm_ms=out[0], gemm_flops=out[1], gemm_launches=int(out[2]), attn_ms=out[3], attn_flops=out[4],
                     attn_launches=int(out[5]))
 
     def profile_list(self, cap: int = 4096):
         """[(ms, flops, kind)] of the launches recorded since profile(True), in launch order (kind 0 GEMM, 1 attention)."""
         ms, fl, kd = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_int * cap)()
-        n = _lib.lib().s3r_engine_profile_list(self._h, ms, fl, kd, cap)
+        with self._on():
+            n = _lib.lib().s3r_engine_profile_list(self._h, ms, fl, kd, cap)
         if n < 0:
             _lib.check(n, "profile_list")
         return [(ms[i], fl[i], kd[i]) for i in range(min(n, cap))]

@@ -51,7 +51,9 @@ def build_param_tree(root: nn.Module, keys_shapes: dict, prefix: str = ""):
             mod = mod._modules[p]
         canon = synth.canonical_key(key)
         if canon not in shared:
-            shared[canon] = nn.Parameter(torch.empty(tuple(shape), dtype=torch.float32), requires_grad=False)
+            # zero-filled, never uninitialised memory; `Spann3R._init_like_reference` gives the keys a DUSt3R
+            # checkpoint does not cover the reference constructors' default init
+            shared[canon] = nn.Parameter(torch.zeros(tuple(shape), dtype=torch.float32), requires_grad=False)
         mod.register_parameter(parts[-1], shared[canon])
     return root
 
@@ -81,6 +83,8 @@ class AsymmetricCroCo3DStereo(ParamModule):
             for k, v in ckpt.items():
                 if k.startswith("dec_blocks"):
                     new[k.replace("dec_blocks", "dec_blocks2")] = v
+        if self._owner is not None:
+            self._owner._packed_dirty = True
         return super().load_state_dict(new, strict=strict, **kw)
 
     # -- stage methods, same names / argument meaning as the reference -------------------------------
@@ -93,10 +97,18 @@ class AsymmetricCroCo3DStereo(ParamModule):
     def _decoder(self, f1, pos1, f2, pos2):
         """dust3r/model.py:186-205 -> (dec1, dec2), 13 tensors each ([f_enc, d1..d12], d12 normed)."""
         o = self._owner
-        if o._hw is None or (o._hw[0] // 16) * (o._hw[1] // 16) != f1.shape[1]:
-            raise RuntimeError("_decoder needs the image size of the features it is given: call _encode_image (or the "
-                               "model) on that resolution first -- the token count alone does not determine (H, W)")
-        eng = o._engine_for(f1.shape[0], o._hw[0], o._hw[1])
+        # the patch grid comes from the POSITIONS, as in the reference (its RoPE is position-driven): 768 tokens can be
+        # 24 x 32 or 32 x 24, and only pos tells which
+        grids = []
+        for pos in (pos1, pos2):
+            if pos is None:
+                raise RuntimeError("_decoder needs the token positions (pos1, pos2) returned by _encode_image")
+            gh, gw = int(pos[..., 0].max()) + 1, int(pos[..., 1].max()) + 1
+            grids.append((gh, gw))
+        if grids[0] != grids[1] or grids[0][0] * grids[0][1] != f1.shape[1] or f2.shape[1] != f1.shape[1]:
+            raise RuntimeError(f"_decoder: positions describe patch grids {grids} but the features have "
+                               f"{f1.shape[1]} / {f2.shape[1]} tokens (both views must share one grid)")
+        eng = o._engine_for(f1.shape[0], 16 * grids[0][0], 16 * grids[0][1])
         dec_all = eng.decode(f1.contiguous(), f2.contiguous(), want_all=True)
         dec1 = [f1] + [dec_all[l, 0] for l in range(12)]
         dec2 = [f2] + [dec_all[l, 1] for l in range(12)]
@@ -193,7 +205,7 @@ class SpatialMemory:
             self._sim_host = torch.empty(1, dtype=torch.float32, pin_memory=True)
         self._sim_host.copy_(mean_corr.max().reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(torch.cuda.current_stream(mean_corr.device))
         return ev
 
     def check_sim_finish(self, pending, thresh=0.7):
@@ -266,11 +278,11 @@ class Spann3R(ParamModule):
         self._enc_engines = {}
         self._streams = None
         self._packed = None
-        self._packed_version = None
+        self._packed_dirty = True
         self._engines = {}
         self._pos_cache = {}
-        self._hw = None
         if dus3r_name is not None:
+            self._init_like_reference()
             self._load_dust3r(dus3r_name)
 
     # -- checkpoint plumbing -----------------------------------------------------------------------
@@ -291,12 +303,43 @@ class Spann3R(ParamModule):
         self.pos_patch_embed.proj.weight.data.copy_(self.dust3r.patch_embed.proj.weight.data)
         self.pos_patch_embed.proj.bias.data.copy_(self.dust3r.patch_embed.proj.bias.data)
 
-    def _version(self):
-        return tuple(p._version for p in self.parameters()) + (str(next(self.parameters()).device),)
+    @torch.no_grad()
+    def _init_like_reference(self):
+        """The parameters a DUSt3R checkpoint does NOT cover get what the reference's constructors give them
+        (spann3r/model.py:228-261: stock nn.Linear / nn.LayerNorm / Block init), so that a `strict=False` or partial
+        Spann3R checkpoint load never runs on zeros: LayerNorm weight 1 / bias 0, Linear and conv weights
+        kaiming_uniform(a=sqrt(5)), biases U(+-1/sqrt(fan_in))."""
+        import math
+        for name, p in self.named_parameters():
+            if name.startswith("dust3r."):
+                continue
+            leaf = name.split(".")[-1]
+            mod = name.split(".")[-2]
+            is_norm = mod.startswith("norm") or mod.endswith("_norm") or mod.endswith("norm")
+            if is_norm:
+                p.fill_(1.0 if leaf == "weight" else 0.0)
+            elif leaf == "weight":
+                nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+            else:
+                w = dict(self.named_parameters())[name[: -len("bias")] + "weight"]
+                fan_in = w[0].numel()
+                p.uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+
+    # The packed device copy of the weights is rebuilt when the parameters may have changed: load_state_dict, any
+    # _apply (.to / .cuda / .float) and an explicit invalidate_packed() after in-place edits of `.data`.
+    def invalidate_packed(self):
+        self._packed_dirty = True
+
+    def load_state_dict(self, *a, **k):
+        self._packed_dirty = True
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed_dirty = True
+        return super()._apply(fn, *a, **k)
 
     def _weights(self) -> PackedWeights:
-        v = self._version()
-        if self._packed is None or v != self._packed_version:
+        if self._packed is None or self._packed_dirty:
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("spann3r_b200.Spann3R runs on a B200 only: call .to('cuda') first (no CPU path)")
@@ -304,12 +347,11 @@ class Spann3R(ParamModule):
             self._enc_engines.clear()
             self._packed = None
             self._packed = PackedWeights(self.state_dict(), device=dev)
-            self._packed_version = v
+            self._packed_dirty = False
         return self._packed
 
     def _engine_for(self, B, H, W, n_frames=2, encode_only=False) -> Engine:
         w = self._weights()
-        self._hw = (H, W)
         max_images = max(2 * B, min(n_frames * B, self.max_encode_batch * B))
         key = (B, H, W)
         eng = self._engines.get(key)

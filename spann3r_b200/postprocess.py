@@ -30,13 +30,16 @@ def estimate_focal_knowing_depth(pts3d: torch.Tensor, pp, focal_mode: str = "med
     focal = torch.empty(B, dtype=torch.float32, device=pts3d.device)
     if focal_mode == "median":      # nanmedian of the per-pixel votes: an exact selection, bit-identical to the reference
         scratch = torch.empty(B * 260, dtype=torch.int32, device=pts3d.device)
-        _lib.check(_lib.lib().s3r_focal_median(_lib.ptr(pts3d), B, H, W, ppx, ppy, lo,
-                                               max_focal * base if math.isfinite(max_focal) else float("inf"),
-                                               _lib.ptr(scratch), _lib.ptr(focal), _lib.stream_ptr()), "s3r_focal_median")
+        with _lib.on_device(pts3d):
+            _lib.check(_lib.lib().s3r_focal_median(_lib.ptr(pts3d), B, H, W, ppx, ppy, lo,
+                                                   max_focal * base if math.isfinite(max_focal) else float("inf"),
+                                                   _lib.ptr(scratch), _lib.ptr(focal), _lib.stream_ptr(pts3d.device)),
+                       "s3r_focal_median")
         return focal
     scratch = torch.empty(B * 148 * 2, dtype=torch.float32, device=pts3d.device)
-    _lib.check(_lib.lib().s3r_focal_weiszfeld(_lib.ptr(pts3d), B, H, W, ppx, ppy, 10, lo, hi, _lib.ptr(scratch),
-                                              _lib.ptr(focal), _lib.stream_ptr()), "s3r_focal_weiszfeld")
+    with _lib.on_device(pts3d):
+        _lib.check(_lib.lib().s3r_focal_weiszfeld(_lib.ptr(pts3d), B, H, W, ppx, ppy, 10, lo, hi, _lib.ptr(scratch),
+                                                  _lib.ptr(focal), _lib.stream_ptr(pts3d.device)), "s3r_focal_weiszfeld")
     return focal
 
 
@@ -77,7 +80,8 @@ def solve_pnp_ransac(pts3d: torch.Tensor, camera_matrix, image_points: torch.Ten
     ws = torch.empty(int(L.s3r_pnp_workspace_bytes(B, int(iterations_count))), dtype=torch.uint8, device=pts3d.device)
     out = torch.empty(B, 18, dtype=torch.float64, device=pts3d.device)
     mask = torch.empty(B, n, dtype=torch.uint8, device=pts3d.device)
-    _lib.check(L.s3r_pnp_ransac(_lib.ptr(pts3d), _lib.ptr(image_points), B, n, width, fx, fy, cx, cy,
-                                float(reprojection_error), int(iterations_count), int(refine_iters), int(seed),
-                                _lib.ptr(ws), _lib.ptr(out), _lib.ptr(mask), _lib.stream_ptr()), "s3r_pnp_ransac")
+    with _lib.on_device(pts3d):
+        _lib.check(L.s3r_pnp_ransac(_lib.ptr(pts3d), _lib.ptr(image_points), B, n, width, fx, fy, cx, cy,
+                                    float(reprojection_error), int(iterations_count), int(refine_iters), int(seed),
+                                    _lib.ptr(ws), _lib.ptr(out), _lib.ptr(mask), _lib.stream_ptr(pts3d.device)), "s3r_pnp_ransac")
     return out[:, 17] > 0.5, out[:, 12:15], out[:, 9:12], mask.view(out_shape).bool()

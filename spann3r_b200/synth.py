@@ -7,7 +7,7 @@ and on the GPU box (where /root/reference does not exist), so every tensor is dr
 its own `torch.Generator` seeded by (seed, crc32(key)): the result depends only on the key
 name, the shape and the torch version, not on construction order.
 
-The key/shape inventory is `tests/golden/state_dict_spec.json`, dumped from the real
+The key/shape inventory is `spann3r_b200/state_dict_spec.json` (package data), dumped from the real
 reference model by `tools/make_golden.py` (1101 keys for Spann3R).
 
 Init rules follow what the reference constructors do (so activations are conditioned like
@@ -31,8 +31,7 @@ import zlib
 
 import torch
 
-_SPEC_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                          "tests", "golden", "state_dict_spec.json")
+_SPEC_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "state_dict_spec.json")
 
 
 def load_spec(path: str = _SPEC_PATH) -> dict:

@@ -33,6 +33,9 @@ CASES = [
     # portrait frames: heads at (H, W), outputs / value-encoder input transposed to landscape (dust3r/utils/misc.py:66-94)
     ("seq_288x224_4f_sharp.npz", True, 4, 288, 224),
     ("seq_512x384_3f_sharp.npz", True, 3, 512, 384),
+    # BASELINE config 2 itself (the headline: 10 x 512x384, B = 1) on both checkpoints of SURVEY.md §8d, real-reference goldens
+    ("cfg2_384x512_10f_sharp.npz", True, 10, 384, 512),
+    ("cfg2_384x512_10f_raw.npz", False, 10, 384, 512),
 ]
 
 
@@ -52,6 +55,7 @@ def test_forward_matches_reference_golden(models, fname, sharpen, nf, H, W):
     for i, (_, r2) in enumerate(preds_all):
         for k, v in r2.items():
             errs[f"preds_all/{i}/res2/{k}"] = rel_l2(v[:, ::s, ::s].cpu(), g[f"preds_all/{i}/res2/{k}"])
+    assert all(bool(torch.isfinite(v).all()) for p in preds for v in p.values())
     errs["mem_k"] = rel_l2(mem.mem_k[:, ::7, ::8].cpu(), g["mem/mem_k_sub"])
     errs["mem_v"] = rel_l2(mem.mem_v[:, ::7, ::8].cpu(), g["mem/mem_v_sub"])
     errs["mem_attn"] = rel_l2(mem.mem_attn.cpu(), g["mem/mem_attn"])
@@ -172,11 +176,35 @@ def test_batched_sequences_match_single(models):
             assert rel_l2(pboth[i][k][1:2].cpu(), pb[i][k].cpu()) < 1e-4, (i, k)
 
 
+def test_config3_per_gpu_shape_b8_lockstep_512x384(models):
+    """BASELINE config[2]'s per-GPU shape: 8 independent 10-frame 512x384 sequences (seeds 100 s + i)
+    advanced in lockstep as ONE B = 8 call == each sequence run alone at B = 1; sequence 0 (seeds 1..10) is also the
+    real-reference golden of config 2."""
+    from spann3r_b200 import synth
+    m = models[True]
+    seqs = [synth.make_frames(10, 384, 512, seed0=100 * s + 1) for s in range(8)]
+    both = [{"img": torch.cat([q[f]["img"] for q in seqs])} for f in range(10)]
+    pall, _ = m(both)
+    pall = [{k: v.clone() for k, v in p.items()} for p in pall]
+    worst = 0.0
+    for s_, q in enumerate(seqs):
+        ps, _ = m(q)
+        for i in range(10):
+            for k in ps[i]:
+                worst = max(worst, rel_l2(pall[i][k][s_: s_ + 1].cpu(), ps[i][k].cpu()))
+    print("B=8 lockstep vs B=1, worst rel-L2 over 8 x 10 frames: %.2e" % worst)
+    assert worst < 2e-4        # different tile shapes / summation order at B = 8, same arithmetic
+    g = np.load(os.path.join(GOLDEN, "cfg2_384x512_10f_sharp.npz"))
+    s = int(g["meta/px_stride"])
+    for i, p in enumerate(pall):
+        for k, v in p.items():
+            assert rel_l2(v[0:1, ::s, ::s].cpu(), g[f"preds/{i}/{k}"]) < TOL, (i, k)
+
+
 def test_long_sequence_with_prune_vs_oracle(models):
     """30 frames at 224x224 (196 tokens/frame): the bank passes long_mem_size=4000 and is pruned (top-k by attention
-    weight, spann3r/model.py:185-210).  Compared with the oracle run on the same GPU in strict fp32; the top-k
-    membership near the cut can legitimately flip on 1e-5-level differences, so the bar is
-    the north-star 1e-3 on the median frame and 5e-3 on the worst."""
+    weight, spann3r/model.py:185-210).  Compared with the oracle run on the same GPU in strict fp32; every frame
+    is held to the north-star 1e-3 (round 1 measured <= 4.9e-4 on every frame)."""
     from oracle import spann3r_oracle as orc
     from spann3r_b200 import synth
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -195,8 +223,7 @@ def test_long_sequence_with_prune_vs_oracle(models):
         errs.append(rel_l2(p[k].cpu(), r[k].cpu()))
     errs_sorted = sorted(errs)
     print("per-frame rel-L2:", ["%.1e" % e for e in errs])
-    assert errs_sorted[len(errs) // 2] < 1e-3, errs
-    assert errs_sorted[-1] < 5e-3, errs
+    assert errs_sorted[-1] < TOL, errs
 
 
 def test_dust3r_pairwise_forward_and_stage_api(models):

@@ -58,6 +58,32 @@ def test_forward_matches_reference(fname, sharpen, nf, H, W):
     assert rel_l2(_sub_tokens(trace[0]["cur_v"]), g["act/value_out#0"]) < TOL
 
 
+# BASELINE config 2 itself -- the headline 10-frame 512x384 sequence -- on both checkpoints SURVEY.md §8d names (sharpened =
+# headline; raw = ill-conditioned memory reads from the 7th frame on: ~10 surviving weights per row after the 5e-4 cut).
+CFG2_CASES = [("cfg2_384x512_10f_sharp.npz", True, 2e-5), ("cfg2_384x512_10f_raw.npz", False, 2e-4)]
+
+
+@pytest.mark.parametrize("fname,sharpen,tol", CFG2_CASES)
+def test_config2_headline_matches_reference(fname, sharpen, tol):
+    g = np.load(os.path.join(GOLDEN, fname))
+    sd = get_state_dict(sharpen)
+    preds, preds_all, mem = orc.forward(sd, synth.make_frames(10, 384, 512), return_memory=True)
+    s = int(g["meta/px_stride"])
+    worst = 0.0
+    for i, p in enumerate(preds):
+        assert set(p.keys()) == {k.split("/")[-1] for k in g.files if k.startswith(f"preds/{i}/")}
+        for k, v in p.items():
+            assert torch.isfinite(v).all()
+            worst = max(worst, rel_l2(v[:, ::s, ::s], g[f"preds/{i}/{k}"]))
+    for i, (_, r2) in enumerate(preds_all):
+        for k, v in r2.items():
+            worst = max(worst, rel_l2(v[:, ::s, ::s], g[f"preds_all/{i}/res2/{k}"]))
+    print(fname, "worst rel-L2 %.2e" % worst)
+    assert worst < tol, worst
+    assert mem.mem_k.shape[1] == 9 * 768 and np.array_equal(mem.mem_count.numpy(), g["mem/mem_count"])
+    assert rel_l2(mem.mem_attn, g["mem/mem_attn"]) < 10 * tol
+
+
 # Portrait frames (the landscape wrapper transposes every head output, dust3r/utils/misc.py:66-94) and the
 # mem_pos_enc=True constructor variant (RoPE in the value encoder): real-reference runs without activation hooks.
 VARIANT_CASES = [

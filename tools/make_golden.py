@@ -9,7 +9,7 @@ fixtures it writes into tests/golden/.
     python tools/make_golden.py --only spec
 
 Outputs
-  tests/golden/state_dict_spec.json   key -> shape of the reference Spann3R state dict
+  spann3r_b200/state_dict_spec.json   key -> shape of the reference Spann3R state dict
   tests/golden/cfg1_224_2f_raw.npz    BASELINE config 1 (2 x 224x224), raw random-init weights
   tests/golden/seq_224_4f_sharp.npz   4 x 224x224, sharpened weights (two memory reads)
   tests/golden/seq_384x512_3f_sharp.npz  3 x 384x512, sharpened, outputs sub-sampled (::4, ::4)
@@ -17,6 +17,8 @@ Outputs
   tests/golden/seq_288x224_4f_sharp.npz  PORTRAIT 4 x (H=288, W=224): transpose_to_landscape (dust3r/utils/misc.py:66-94), outputs (::2, ::2)
   tests/golden/seq_512x384_3f_sharp.npz  PORTRAIT 3 x (H=512, W=384), outputs sub-sampled (::4, ::4)
   tests/golden/seq_224_3f_sharp_mempos.npz  3 x 224x224 with Spann3R(mem_pos_enc=True) (RoPE inside the value encoder)
+  tests/golden/cfg2_384x512_10f_sharp.npz  BASELINE config 2 exactly (10 x 384x512, sharpened ckpt), outputs (::8, ::8)   [--only cfg2]
+  tests/golden/cfg2_384x512_10f_raw.npz    the same on the RAW random-init checkpoint (report both)            [--only cfg2]
 Each npz also holds sub-sampled per-stage activations captured with forward hooks so that a
 parity failure can be localised to a stage.
 """
@@ -41,7 +43,7 @@ def build_reference(seed=0, sharpen=False, mem_pos_enc=False):
     from spann3r.model import Spann3R  # noqa  (reference)
     from spann3r_b200 import synth
 
-    spec_path = os.path.join(GOLD, "state_dict_spec.json")
+    spec_path = os.path.join(REPO, "spann3r_b200", "state_dict_spec.json")
     tmp = "/tmp/fake_dust3r.pth"
     if not os.path.exists(spec_path):
         # bootstrap: build once with whatever init to learn the key inventory
@@ -178,6 +180,11 @@ def main():
         m = build_reference(sharpen=True, mem_pos_enc=True)
         run(m, synth.make_frames(3, 224, 224), os.path.join(GOLD, "seq_224_3f_sharp_mempos.npz"), px_stride=2, hooks=False)
         del m
+    if args.only in ("all", "cfg2"):   # the headline config itself, both checkpoints (~10 CPU-minutes each on 8 cores)
+        for sharpen, tag in ((True, "sharp"), (False, "raw")):
+            m = build_reference(sharpen=sharpen)
+            run(m, synth.make_frames(10, 384, 512), os.path.join(GOLD, f"cfg2_384x512_10f_{tag}.npz"), px_stride=8, hooks=False)
+            del m
     if args.only in ("all", "seq224", "seq512", "offline", "portrait"):
         m = build_reference(sharpen=True)
         if args.only in ("all", "portrait"):
