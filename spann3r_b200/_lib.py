@@ -56,6 +56,8 @@ _PROTOS = {
     "s3r_gemm_tile_n": (_i, [C.POINTER(GemmDesc)]),
     "s3r_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "s3r_conf_score": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "s3r_dropout_mask": (_i, [_vp, C.c_longlong, C.c_ulonglong, _f, _vp]),
+    "s3r_set_option": (_i, [C.c_char_p, _i]),
     "s3r_focal_weiszfeld": (_i, [_vp, _i, _i, _i, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
     "s3r_focal_median": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
     "s3r_pnp_workspace_bytes": (C.c_size_t, [_i, _i]),
@@ -140,13 +142,17 @@ def on_device(t_or_dev):
 # ------------------------------------------------------------------------------------------------
 # tensor-level helpers (op level; the model-level fast path lives in engine.py)
 # ------------------------------------------------------------------------------------------------
-def split(x: torch.Tensor, relu: bool = False):
-    """fp32 [..., C] contiguous -> (hi, lo) bf16 planes of the same shape."""
+def split(x: torch.Tensor, relu: bool = False, out=None):
+    """fp32 [..., C] contiguous -> (hi, lo) bf16 planes of the same shape (`out`: existing planes to overwrite)."""
     assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
     c = x.shape[-1]
     rows = x.numel() // c
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty_like(hi)
+    if out is not None:
+        hi, lo = out
+        assert hi.numel() == x.numel() and lo.numel() == x.numel() and hi.dtype == torch.bfloat16 and hi.device == x.device
+    else:
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
     with on_device(x):
         check(lib().s3r_split(ptr(x), c, ptr(hi), ptr(lo), c, 0, rows, c, int(relu), stream_ptr(x.device)), "s3r_split")
     return hi, lo
@@ -207,4 +213,14 @@ def conf_score(conf: torch.Tensor) -> torch.Tensor:
     out = torch.empty(1, dtype=torch.float32, device=conf.device)
     with on_device(conf):
         check(lib().s3r_conf_score(ptr(conf), conf.numel(), ptr(scratch), ptr(out), stream_ptr(conf.device)), "s3r_conf_score")
+    return out
+
+
+def dropout_mask(shape, seed: int, p: float, device) -> torch.Tensor:
+    """Keep-scale (0 or 1 / (1 - p)) of every element of a [..., len] attention tensor under the Philox mask the
+    training-mode memory read applies for `seed` (s3r_engine_memory_read_train); flat index = row-major position."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    with on_device(out):
+        check(lib().s3r_dropout_mask(ptr(out), out.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, float(p), stream_ptr(out.device)),
+              "s3r_dropout_mask")
     return out

@@ -39,7 +39,7 @@ def _newer(src_list, target) -> bool:
 
 def build(force: bool = False, verbose: bool = True, defines=(), lib: str = LIB, obj_dir: str = OBJ) -> str:
     """defines / lib / obj_dir: build an A/B variant next to the shipped library, e.g.
-    `python -m spann3r_b200.build --variant attn56 -DS3R_ATTN_PRODUCER_REGS=56` -> ab/libspann3r_b200_attn56.so (git-ignored,
+    `python -m spann3r_b200.build --variant NAME -DSOME_MACRO=1` -> ab/libspann3r_b200_NAME.so (git-ignored,
     travels with gpurun; select it with S3R_LIB=...).  The default build takes no defines."""
     return _build(force, verbose, tuple(defines), lib, obj_dir)
 

@@ -17,11 +17,10 @@
 #include <cstdlib>
 #include <cstring>
 
-#ifndef S3R_ATTN_PRODUCER_REGS
+// Registers left to the TMA / MMA warpgroup after setmaxnreg.dec.  40 is the verified build; 64 (128 x 64 + 256 x 224 = the
+// whole 64 K file) was built and run on a B200 in round 2 to remove the pair-tile variant's ~0.2 KB spill: the kernel
+// faults ("unspecified launch failure", gpurun_out/r2a_ab_attn64.err), so the knob is gone and the spill stays.
 #define S3R_ATTN_PRODUCER_REGS 40
-#endif
-static_assert(S3R_ATTN_PRODUCER_REGS % 8 == 0 && S3R_ATTN_PRODUCER_REGS >= 24 && S3R_ATTN_PRODUCER_REGS <= 64,
-              "setmaxnreg takes a multiple of 8; 128 x R + 256 x 224 registers must fit the 64 K file");
 
 namespace s3r {
 
@@ -127,8 +126,6 @@ __global__ void __launch_bounds__(attn::kThreads, 1) attention_kernel(const __gr
 
   // register re-balancing: the TMA / MMA warpgroup needs few registers, each softmax thread holds a 128-key row
   if (warp < 4) {
-  // S3R_ATTN_PRODUCER_REGS (build-time, default 40 = the verified build): registers left to this warpgroup; 128 x R + 256 x 224
-  // must fit the 64 K register file (R <= 64).  profiles/r1_ptxas_resources.md: the pair-tile variant spills ~0.2 KB at 40.
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S3R_ATTN_PRODUCER_REGS));
   if (warp == 0) {
     if (lane == 0) {
@@ -423,7 +420,7 @@ int attn_plan_init(AttnPlan* plan, const float* q, const float* k, const float* 
   a.nq = nq; a.nk = nk; a.heads = heads;
   // many-wave launches (the batched encoder: 960 CTAs on 148 SMs) take two query tiles per CTA
   const int q_tiles = (nq + BQ - 1) / BQ;
-  static const int pair_on = getenv("S3R_ATTN_PAIR") ? atoi(getenv("S3R_ATTN_PAIR")) : 1;   // 0: A/B switch
+  const int pair_on = options().attn_pair;
   plan->pair = (pair_on && q_tiles % 2 == 0 && (long long)q_tiles * BH >= 3 * 148) ? 1 : 0;
   plan->grid = dim3(plan->pair ? q_tiles / 2 : q_tiles, BH);
   plan->flops = 4.0 * BH * (double)nq * nk * 64;

@@ -179,6 +179,25 @@ int s3r_conf_score(const float* conf, int64_t n, float* scratch256, float* out, 
   return launch_conf_score(conf, n, scratch256, out, S(stream));
 }
 
+int s3r_set_option(const char* name, int value) {
+  s3r::Options& o = s3r::options();
+  if (!name) { set_error("s3r_set_option: null name"); return -1; }
+  if (!strcmp(name, "gemm2")) o.gemm2 = value;
+  else if (!strcmp(name, "gemm2_64")) o.gemm2_64 = value;
+  else if (!strcmp(name, "prefetch_b")) o.prefetch_b = value;
+  else if (!strcmp(name, "attn_pair")) o.attn_pair = value;
+  else { set_error("s3r_set_option: unknown option '%s' (gemm2, gemm2_64, prefetch_b, attn_pair)", name); return -1; }
+  return 0;
+}
+
+int s3r_dropout_mask(float* out, long long n, unsigned long long seed, float p, void* stream) {
+  if (!out && n > 0) {
+    set_error("s3r_dropout_mask: null output");
+    return -1;
+  }
+  return launch_dropout_mask(out, n, seed, p, S(stream));
+}
+
 int s3r_attention(const float* q, const float* k, const float* vt, int bh, int heads, int nq, int nk, int nk_pad,
                   void* o_hi, void* o_lo, float* o_f32, int64_t ldo, void* stream) {
   return launch_attention(q, k, vt, bh, heads, nq, nk, nk_pad, B(o_hi), B(o_lo), o_f32, ldo, S(stream));

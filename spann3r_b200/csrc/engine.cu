@@ -34,6 +34,7 @@ inline Planes WP(const s3r_planes& p) {
 
 struct Geom {
   int groups = 1, NB = 1, H = 1, W = 1, Kc = 0, taps = 1, N = 0, force_bn = 0;
+  int b_static = 1;   // B = packed weights (everything except the two memory-read GEMMs, whose B is the bank)
   long long lda = 0, ldb = 0, b_group_rows = 0;
 };
 
@@ -155,6 +156,7 @@ struct s3r_engine {
       int r = gemm_plan_init(&pc.gemms.back(), A.hi, A.lo, Bw.hi, Bw.lo, g.groups, g.NB, g.H, g.W, g.Kc, g.taps, g.N,
                              e.epi == EPI_HEADTAIL ? 1128 : g.force_bn, g.lda, g.ldb, g.b_group_rows);
       if (r) return r;
+      pc.gemms.back().b_static = (g.b_static && options().prefetch_b) ? 1 : 0;   // decided when the plan is built
     }
     if (pc.gc >= pc.gemms.size()) {
       set_error("engine: plan cache out of sync");
@@ -179,6 +181,7 @@ struct s3r_engine {
     a.ln_stats = e.ln_stats; a.ln_np = e.ln_np; a.ln_eps = e.ln_eps; a.ln_cs = e.ln_cs; a.a_swap = e.a_swap;
     a.swap_col0 = e.swap_col0;
     a.stats_out = e.stats_out;
+    a.b_static = p.b_static;
     flops += p.flops;
     ++launches;
     if (!profiling) return gemm_launch(p, st);
@@ -795,8 +798,19 @@ int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, in
 // ------------------------------------------------------------------------------------------------
 int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float* out,
                            void* stream) {
+  return s3r_engine_memory_read_train(e, bank, feat, thresh, 0.f, 0ull, out, stream);
+}
+
+// training-mode read (spann3r/model.py:474 attn_thresh = 0, :167-168 dropout on the attention weights): same launches, the
+// softmax stage additionally applies the Philox keep-scale of (seed, row * M + column)
+int s3r_engine_memory_read_train(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float drop_p,
+                                 unsigned long long seed, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S3R_ENGINE_DEVICE(e, "s3r_engine_memory_read");
+  if (!(drop_p >= 0.f && drop_p < 1.f)) {
+    set_error("s3r_engine_memory_read: dropout probability %g outside [0, 1)", (double)drop_p);
+    return -1;
+  }
   const int B = e->B, N = e->N, M = bank->len, cap = bank->cap;
   if (M <= 0 || M > cap || cap % 8 != 0) {
     set_error("s3r_engine_memory_read: bad bank (len=%d cap=%d; cap must be a multiple of 8)", M, cap);
@@ -821,7 +835,7 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
   int r;
   if ((r = e->ln(feat, e->w.norm_q, 0, 0, 1e-5f, R, 1024, nullptr, 0, e->Qn, 1024, 0, 0, st))) return r;
   {  // S = LN_q(feat) . LN_k(mem_k)^T, one group per batch item (each sequence has its own bank)
-    Geom g; g.groups = B; g.W = N; g.Kc = 1024; g.N = M; g.b_group_rows = cap;
+    Geom g; g.groups = B; g.W = N; g.Kc = 1024; g.N = M; g.b_group_rows = cap; g.b_static = 0;
     Epi ep; ep.out = e->Sm; ep.ldo = e->mem_cap;
     if ((M + 31) / 32 * 32 > cap) {  // the epilogue writes whole 32-column chunks
       set_error("s3r_engine_memory_read: bank capacity %d must cover len %d rounded up to 32", cap, M);
@@ -831,12 +845,13 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
     if ((r = e->gemm(pc, e->Qn, Kn, g, ep, st))) return r;
   }
   e->launches += 3;
-  if ((r = launch_mem_softmax(e->Sm, e->mem_cap, R, M, Mpad, 1.0f / 32.0f, thresh, e->Pm.hi, e->Pm.lo, e->mem_cap, st)))
+  if ((r = launch_mem_softmax(e->Sm, e->mem_cap, R, M, Mpad, 1.0f / 32.0f, thresh, e->Pm.hi, e->Pm.lo, e->mem_cap, st,
+                              drop_p, seed)))
     return r;
   // the fp32 scores are dead once the softmax has run: Sm doubles as the [B, chunks, mem_cap] partial-sum scratch
   if ((r = launch_mem_colsum(e->Pm.hi, e->Pm.lo, e->mem_cap, B, N, M, bank->attn, cap, e->Sm, e->mem_cap, st))) return r;
   {  // out = attn . LN_v(mem_v) + feat
-    Geom g; g.groups = B; g.W = N; g.Kc = M; g.N = 1024; g.lda = e->mem_cap; g.ldb = cap; g.b_group_rows = 1024;
+    Geom g; g.groups = B; g.W = N; g.Kc = M; g.N = 1024; g.lda = e->mem_cap; g.ldb = cap; g.b_group_rows = 1024; g.b_static = 0;
     Epi ep; ep.res1 = feat; ep.ldr1 = 1024; ep.out = out; ep.ldo = 1024;
     Planes Vt; Vt.hi = (__nv_bfloat16*)bank->vnt_hi; Vt.lo = (__nv_bfloat16*)bank->vnt_lo;
     if ((r = e->gemm(pc, e->Pm, Vt, g, ep, st))) return r;

@@ -99,7 +99,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
   if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
-  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Weights do not depend on the previous kernel: the producer stages the B tiles of the first ring pass of this CTA's first
+  // tile BEFORE the dependency wait (their HBM / L2 latency overlaps the previous kernel's tail); the A tiles of those
+  // stages follow after the wait, on the same full barrier (expect_tx covers the whole stage).
+  int pre_b = 0;
+  if (warp == 0 && args.b_static && (int)blockIdx.x < total_tiles) {
+    const int tile = blockIdx.x;
+    const int g = tile / tiles_per_group;
+    const int nt = (tile - g * tiles_per_group) % n_tiles;
+    const int brow = g * args.b_group_rows + nt * BN;
+    pre_b = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+    if (lane == 0) {
+      for (int kb = 0; kb < pre_b; ++kb) {
+        const int tap = kb / args.kpt, kc = (kb - tap * args.kpt) * BK;
+        uint8_t* s = smem + kb * Cfg::STAGE;
+        mbar_arrive_expect_tx(&full_bar[kb], Cfg::STAGE);
+        tma_load_3d(s + 2 * Cfg::A_TILE, &args.tmB_hi, &full_bar[kb], kc, tap, brow);
+        tma_load_3d(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, &full_bar[kb], kc, tap, brow);
+      }
+    }
+    __syncwarp();
+  }
+  pdl_wait();  // everything above overlapped the previous kernel's tail; activations are touched only below
   if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
 
   if (warp == 0) {
@@ -125,14 +146,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16x3_kernel(const __gri
         int tap = 0, kc = 0, dx = (args.taps == 9) ? -1 : 0, dy = dx;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool b_done = (tile == (int)blockIdx.x) && (kb < pre_b);   // B (and the expect_tx) went out before the wait
           if (elect_one()) {
             const uint32_t s = smem_u + stage * Cfg::STAGE;
             const uint32_t fb = full_u + stage * 8;
-            mbar_arrive_expect_tx_u(fb, Cfg::STAGE);
+            if (!b_done) mbar_arrive_expect_tx_u(fb, Cfg::STAGE);
             tma_load_4d_u(s, &args.tmA_hi, fb, kc, w0 + dx, h0 + dy, img);
             tma_load_4d_u(s + Cfg::A_TILE, &args.tmA_lo, fb, kc, w0 + dx, h0 + dy, img);
-            tma_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
-            tma_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+            if (!b_done) {
+              tma_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
+              tma_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+            }
           }
           __syncwarp();
           kc += BK;
@@ -356,6 +380,18 @@ static int next_pow2(int x) {
   return p;
 }
 
+Options& options() {
+  static Options o = [] {
+    Options x;
+    if (const char* e = getenv("S3R_GEMM2")) x.gemm2 = atoi(e);
+    if (const char* e = getenv("S3R_GEMM2_64")) x.gemm2_64 = atoi(e);
+    if (const char* e = getenv("S3R_PREFETCH_B")) x.prefetch_b = atoi(e);
+    if (const char* e = getenv("S3R_ATTN_PAIR")) x.attn_pair = atoi(e);
+    return x;
+  }();
+  return o;
+}
+
 static int g_num_sms[64] = {};   // per device ordinal
 int num_sms() {
   int dev = 0;
@@ -402,7 +438,7 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   const double c64 = waves(m_tiles * nt64, sms) * 0.45;
   const double c128 = (N > 64) ? waves(m_tiles * nt128, sms) * 0.62 : 1e30;
   const bool legal2 = (m_tiles_group % 2 == 0) && N >= 128;
-  static const int g2_mode = getenv("S3R_GEMM2") ? atoi(getenv("S3R_GEMM2")) : 1;   // 0 off, 1 auto, 128/256 fixed
+  const int g2_mode = options().gemm2;   // 0 off, 1 auto, 128/256 fixed
   const double c2128 = (legal2 && g2_mode != 0) ? waves(m_tiles / 2 * nt128, sms / 2) * 0.58 : 1e30;
   int bn = 64, two = 0;
   if (c128 < c64) bn = 128;
@@ -420,7 +456,7 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   // GEMMs of the decoder and value encoder at B = 1, one wave of 144 CTAs, bound by the per-SM operand ingest (DESIGN.md
   // section 4b) -- a 256 x 64 CTA-pair tile keeps the CTA count and the MMA work per SM but stages only half of B per SM:
   // 40 KB instead of 48 KB per k-block.  S3R_GEMM2_64=1 switches those launches over for an in-situ A/B.
-  static const bool pair64 = getenv("S3R_GEMM2_64") && atoi(getenv("S3R_GEMM2_64")) != 0;
+  const bool pair64 = options().gemm2_64 != 0;
   if (pair64 && force_bn == 0 && !two && bn == 64 && m_tiles_group % 2 == 0 && N >= 64) two = 1;
   if (force_bn == 1128) { two = legal2 ? 1 : 0; bn = 128; }   // width 128 (EPI_HEADTAIL), CTA pairs where legal
   else if (force_bn >= 2000) { two = 1; bn = force_bn - 2000; }

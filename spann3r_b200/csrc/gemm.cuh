@@ -44,6 +44,8 @@ struct GemmArgs {
   // ln_stats [A rows, ln_np] = (sum, sum of squares) per 32-column chunk of x, written by the producer's epilogue.
   const float2* ln_stats; int ln_np; float ln_eps;
   const float* ln_cs;                 // [G*N] column sums of W' (as the tensor core sees it: hi + lo planes)
+  int b_static;                       // 1: B is a packed WEIGHT (never written on this stream): the producer may stage its first
+                                      // B tiles before griddepcontrol.wait, while the previous kernel still runs
   int a_swap;                         // 1: group g reads the A rows (and statistics) of group G-1-g (norm_y of the twin decoders)
   int swap_col0;                      // ... for output columns >= swap_col0 only (0 = all); must be a multiple of the tile width
   // Producer side (EPI_PLAIN): write (sum, sum of squares) of every output row chunk, [rows, N/32]
@@ -71,6 +73,7 @@ struct GemmPlan {
   dim3 grid;
   int bn;          // 64 / 128 / 256
   int two_cta;     // 1: 256 x bn tiles on CTA pairs (gemm2.cu)
+  int b_static;    // engine: B is a packed weight and the prefetch option was on when the plan was built
   double flops;    // algorithmic 2*M*N*K (all groups), for roofline accounting
 };
 
@@ -86,6 +89,17 @@ int gemm_plan_init(GemmPlan* plan,
                    long long lda = 0, long long ldb = 0, long long b_group_rows = 0);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm2_launch(const GemmPlan& plan, cudaStream_t stream);   // 2-CTA kernel (gemm2.cu)
+
+// Tuning knobs of the tile planner / producers (s3r_set_option): read when a plan is BUILT, so two engines of one
+// process can be planned under different settings and timed alternately (tools/ab_inproc.py).
+struct Options {
+  int gemm2 = 1;        // CTA-pair GEMM tiles: 0 off, 1 planner's choice, 128 / 256 forced width
+  int gemm2_64 = 0;     // 256 x 64 pair tiles where the planner picks 1-CTA 128 x 64 (N = 768 / 1024 GEMMs at B = 1)
+  int prefetch_b = 1;   // stage the first weight tiles before griddepcontrol.wait
+  int attn_pair = 1;    // two query tiles per CTA for many-wave attention launches
+};
+Options& options();
+int num_sms();
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box);

@@ -165,6 +165,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
+  // B tiles of the first ring pass before the dependency wait (see gemm.cu): weights do not depend on the previous kernel
+  int pre_b = 0;
+  if (warp == 0 && args.b_static && cluster_id < total_pairs) {
+    const int pt = cluster_id;
+    const int g = pt / pairs_per_group;
+    const int nt = (pt - g * pairs_per_group) % n_tiles;
+    const int brow = g * args.b_group_rows + nt * BN + (int)rank * (BN / 2);
+    pre_b = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+    if (lane == 0) {
+      for (int kb = 0; kb < pre_b; ++kb) {
+        const int tap = kb / args.kpt, kc = (kb - tap * args.kpt) * BK;
+        const uint32_t s = smem_u32(smem) + kb * Cfg::STAGE;
+        const uint32_t fb = smem_u32(&full_bar[kb]);
+        if (leader) mbar_arrive_expect_tx_u(fb, 2 * Cfg::STAGE);
+        else mbar_arrive_remote(&full_bar[kb], 0);
+        tma2_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
+        tma2_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+      }
+    }
+    __syncwarp();
+  }
   pdl_wait();
 
   if (warp == 0) {
@@ -190,15 +211,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         int tap = 0, kc = 0, dx = (args.taps == 9) ? -1 : 0, dy = dx;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool b_done = (pt == cluster_id) && (kb < pre_b);   // B (and the arrive) went out before the wait
           if (elect_one()) {
             const uint32_t s = smem_u + stage * Cfg::STAGE;
             const uint32_t fb = full_u + stage * 8;
-            if (leader) mbar_arrive_expect_tx_u(fb, 2 * Cfg::STAGE);
-            else mbar_arrive_remote(&full_bar[stage], 0);
+            if (!b_done) {
+              if (leader) mbar_arrive_expect_tx_u(fb, 2 * Cfg::STAGE);
+              else mbar_arrive_remote(&full_bar[stage], 0);
+            }
             tma2_load_4d_u(s, &args.tmA_hi, fb, kc, w0 + dx, h0 + dy, img);
             tma2_load_4d_u(s + Cfg::A_TILE, &args.tmA_lo, fb, kc, w0 + dx, h0 + dy, img);
-            tma2_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
-            tma2_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+            if (!b_done) {
+              tma2_load_3d_u(s + 2 * Cfg::A_TILE, &args.tmB_hi, fb, kc, tap, brow);
+              tma2_load_3d_u(s + 2 * Cfg::A_TILE + Cfg::B_TILE, &args.tmB_lo, fb, kc, tap, brow);
+            }
           }
           __syncwarp();
           kc += BK;

@@ -47,7 +47,10 @@ int attn_launch(const AttnPlan& plan, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, 
 
 // spatial memory (memory.cu)
 int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int Mpad, float scale, float thresh,
-                       __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st);
+                       __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st, float drop_p = 0.f,
+                       unsigned long long seed = 0);
+// training-mode dropout of the memory read: out[i] = keep-scale (0 or 1 / (1 - p)) of flat element i under `seed`
+int launch_dropout_mask(float* out, long long n, unsigned long long seed, float p, cudaStream_t st);
 // part: scratch of B * ceil(nq/32) rows of ld_part floats (ld_part >= M rounded up to 8)
 int launch_mem_colsum(const __nv_bfloat16* phi, const __nv_bfloat16* plo, long long ldP, int B, int nq, int M,
                       float* mem_attn, long long ld_attn, float* part, long long ld_part, cudaStream_t st);

@@ -16,9 +16,41 @@ namespace s3r {
 // renormalise (spann3r/model.py:157-172) -> split-bf16 planes P[row, 0:Mpad] (zero padded).
 // A row whose every weight is below the threshold divides 0/0 exactly like the reference (NaN).
 // ------------------------------------------------------------------------------------------------
+// Training mode (spann3r/model.py:167-168, nn.Dropout(p) on the softmax output): element (r, i) is kept with probability
+// 1 - p and scaled by 1 / (1 - p).  The keep decision is a pure function of (seed, r * M + i) -- Philox4x32-10, four
+// consecutive elements per counter -- so the backward pass and the tests can regenerate the exact mask
+// (`dropout_mask_kernel`, s3r_dropout_mask).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// keep-scale of element `idx` (0 or 1 / (1 - p)): u = 24 random bits / 2^24 in [0, 1), kept when u >= p
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float keep_scale) {
+  const unsigned long long c = idx >> 2;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  const float u = (float)(w >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? keep_scale : 0.f;
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, unsigned long long seed, float p) {
+  const float ks = 1.0f / (1.0f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = dropout_scale(seed, (unsigned long long)i, p, ks);
+}
+
 __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restrict__ S, long long ldS, int M, int Mpad,
                                                           float scale, float thresh, __nv_bfloat16* __restrict__ phi,
-                                                          __nv_bfloat16* __restrict__ plo, long long ldP) {
+                                                          __nv_bfloat16* __restrict__ plo, long long ldP, float drop_p,
+                                                          unsigned long long seed) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float row[];
@@ -55,9 +87,12 @@ __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restric
   }
   sum = block_reduce(sum, false);
   const float inv = 1.0f / sum;
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   float sum2 = 0.f;
   for (int i = tid; i < M; i += 256) {
     float a = row[i] * inv;
+    // dropout BEFORE the threshold, as in the reference (training runs with attn_thresh = 0)
+    if (drop_p > 0.f) a *= dropout_scale(seed, (unsigned long long)r * (unsigned long long)M + i, drop_p, keep_scale);
     if (thresh > 0.f && a < thresh) a = 0.f;
     row[i] = a;
     sum2 += a;
@@ -79,8 +114,20 @@ __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restric
   }
 }
 
+int launch_dropout_mask(float* out, long long n, unsigned long long seed, float p, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (!(p >= 0.f && p < 1.f)) {
+    set_error("dropout_mask: p=%g outside [0, 1)", (double)p);
+    return -1;
+  }
+  const long long blocks = (n + 255) / 256;
+  dropout_mask_kernel<<<(unsigned)(blocks < 2048 ? blocks : 2048), 256, 0, st>>>(out, n, seed, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -6;
+}
+
 int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int Mpad, float scale, float thresh,
-                       __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st) {
+                       __nv_bfloat16* phi, __nv_bfloat16* plo, long long ldP, cudaStream_t st, float drop_p,
+                       unsigned long long seed) {
   if (rows == 0 || M == 0) return 0;
   const size_t smem = (size_t)M * sizeof(float);
   if (smem > 200 * 1024) {
@@ -92,7 +139,8 @@ int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int
     cudaFuncSetAttribute(mem_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     once.cur() = true;
   }
-  launch_pdl(mem_softmax_kernel, dim3((unsigned)rows), dim3(256), smem, st, S, ldS, M, Mpad, scale, thresh, phi, plo, ldP);
+  launch_pdl(mem_softmax_kernel, dim3((unsigned)rows), dim3(256), smem, st, S, ldS, M, Mpad, scale, thresh, phi, plo, ldP,
+             drop_p, seed);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

@@ -77,6 +77,7 @@ _lib.register_protos({
     "s3r_engine_heads": (_i, [_vp, _vp, _vp, _vp]),
     "s3r_engine_value": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "s3r_engine_memory_read": (_i, [_vp, C.POINTER(Bank), _vp, _f, _vp, _vp]),
+    "s3r_engine_memory_read_train": (_i, [_vp, C.POINTER(Bank), _vp, _f, _f, C.c_ulonglong, _vp, _vp]),
     "s3r_engine_memory_append": (_i, [_vp, C.POINTER(Bank), _vp, _vp, _vp]),
     "s3r_engine_check_sim": (_i, [_vp, C.POINTER(Bank), _vp, _i, _vp, _vp]),
     "s3r_engine_take_flops": (C.c_double, [_vp]),
@@ -123,10 +124,15 @@ def split_bf16_host_rowsum(w: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """Device-resident packed weights + the `s3r_model_w` pointer table."""
 
-    def __init__(self, state_dict: dict, device="cuda"):
+    def __init__(self, state_dict: dict, device="cuda", host_math: bool = True):
+        """host_math=True (inference): the one-time layout arithmetic runs on the CPU copy of the checkpoint.
+        host_math=False (training, where the weights change every optimizer step): the same arithmetic as torch ops on
+        the device tensors, and `refresh()` re-packs IN PLACE (same buffers, so engines and cached tile plans stay valid)."""
         _lib.require_device()
         self.device = torch.device(device)
-        self._keep = []          # tensors the pointer table refers to
+        self.host_math = host_math
+        self._keep = []          # tensors the pointer table refers to, in creation order
+        self._slot = None        # refresh(): index of the next tensor to overwrite (None = allocating)
         self.sd = state_dict
         self.struct = ModelW()
         self.param_bytes = 0
@@ -134,24 +140,50 @@ class PackedWeights:
         del self.sd
         torch.cuda.synchronize(self.device)
 
+    @torch.no_grad()
+    def refresh(self, state_dict: dict):
+        """Re-pack a changed state dict into the existing device buffers (same shapes, same order)."""
+        self.sd = state_dict
+        self._slot = 0
+        self._build()
+        assert self._slot == len(self._keep), "refresh walked a different number of tensors than the first pack"
+        self._slot = None
+        del self.sd
+
     # -- helpers ---------------------------------------------------------------------------------
-    # All one-time layout work (stacking groups, permutes, LayerNorm folding, column sums) is host arithmetic on the
-    # CPU copy of the checkpoint; the device sees one upload per tensor and the library's own split kernel.  (Round 1 did
-    # this with fp64 torch ops on the GPU: ~900 library launches before the first tensor-core kernel.)
+    # Inference: all one-time layout work (stacking groups, permutes, LayerNorm folding, column sums) is host arithmetic
+    # on the CPU copy of the checkpoint; the device sees one upload per tensor and the library's own split kernel.
+    # (Round 1 did this with fp64 torch ops on the GPU: ~900 library launches before the first tensor-core kernel.)
     def _t(self, key):
-        return self.sd[key].detach().to("cpu", torch.float32)
+        return self.sd[key].detach().to("cpu" if self.host_math else self.device, torch.float32)
+
+    def _store(self, t: torch.Tensor) -> torch.Tensor:
+        """Keep `t` alive on the device (first pack) or copy it into the buffer made then (refresh)."""
+        if self._slot is None:
+            t = t.contiguous().to(self.device)
+            self._keep.append(t)
+            return t
+        dst = self._keep[self._slot]
+        self._slot += 1
+        dst.copy_(t.reshape(dst.shape))
+        return dst
 
     def _f32(self, t: torch.Tensor):
-        t = t.contiguous().to(self.device)
-        self._keep.append(t)
-        self.param_bytes += t.numel() * 4
+        t = self._store(t)
+        if self._slot is None:
+            self.param_bytes += t.numel() * 4
         return t.data_ptr()
 
     def _planes(self, w2d: torch.Tensor) -> Planes:
-        hi, lo = _lib.split(w2d.contiguous().to(self.device))
-        self._keep += [hi, lo]
-        self.param_bytes += hi.numel() * 4
         p = Planes()
+        if self._slot is None:
+            hi, lo = _lib.split(w2d.contiguous().to(self.device))
+            self._keep += [hi, lo]
+            self.param_bytes += hi.numel() * 4
+        else:
+            hi, lo = self._keep[self._slot], self._keep[self._slot + 1]
+            self._slot += 2
+            _lib.split(w2d.contiguous().to(self.device), out=(hi, lo))
         p.hi, p.lo = hi.data_ptr(), lo.data_ptr()
         return p
 
@@ -375,11 +407,16 @@ class Engine:
         self._call("s3r_engine_value", "value", _lib.ptr(pts3d), _lib.ptr(feat_k1), flags, _lib.ptr(out))
         return out
 
-    def memory_read(self, bank: MemoryBank, feat, thresh: float):
+    def memory_read(self, bank: MemoryBank, feat, thresh: float, drop_p: float = 0.0, seed: int = 0):
+        """drop_p > 0: the training-mode read (nn.Dropout(drop_p) on the attention weights, Philox mask of `seed`)."""
         self._chk(feat, (self.B, self.N, 1024))
         out = self._new(self.B, self.N, 1024)
         bs = bank.struct()
-        self._call("s3r_engine_memory_read", "memory_read", C.byref(bs), _lib.ptr(feat), float(thresh), _lib.ptr(out))
+        if drop_p > 0.0:
+            self._call("s3r_engine_memory_read_train", "memory_read", C.byref(bs), _lib.ptr(feat), float(thresh), float(drop_p),
+                       int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(out))
+        else:
+            self._call("s3r_engine_memory_read", "memory_read", C.byref(bs), _lib.ptr(feat), float(thresh), _lib.ptr(out))
         return out
 
     def memory_append(self, bank: MemoryBank, feat_k, feat_v):

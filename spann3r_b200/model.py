@@ -7,8 +7,8 @@ same dict keys / shapes -- so `demo.py` / `eval.py` run by changing one import (
 
 The modules below hold parameters only.  All arithmetic runs in libspann3r_b200.so through
 `engine.Engine`; there is no eager-PyTorch, CPU or Triton path -- on a machine without an sm_100
-GPU `forward` raises.  Inference (eval mode) only: the training-mode branches of the reference
-(memory dropout, attn_thresh=0, autograd) are out of scope this round.
+GPU `forward` raises.  Training mode (`train.py`): the same CUDA forward with the reference's
+training branches (attn_thresh=0, memory dropout, ungated add_mem) and a PyTorch-recompute backward (staged).
 `offline_reconstruction` is built on the same engine stages.  Portrait frames follow the
 reference's landscape wrapper (`_to_landscape`); `mem_pos_enc=True` is supported, `use_feat=True` is not.
 """
@@ -53,7 +53,7 @@ def build_param_tree(root: nn.Module, keys_shapes: dict, prefix: str = ""):
         if canon not in shared:
             # zero-filled, never uninitialised memory; `Spann3R._init_like_reference` gives the keys a DUSt3R
             # checkpoint does not cover the reference constructors' default init
-            shared[canon] = nn.Parameter(torch.zeros(tuple(shape), dtype=torch.float32), requires_grad=False)
+            shared[canon] = nn.Parameter(torch.zeros(tuple(shape), dtype=torch.float32))   # trainable, like the reference's
         mod.register_parameter(parts[-1], shared[canon])
     return root
 
@@ -271,14 +271,9 @@ class Spann3R(ParamModule):
         build_param_tree(self, rest)
         self.memory_dropout = memory_dropout
         self.max_encode_batch = max_encode_batch
-        # EXPERIMENT, off by default and not yet measured on a B200: encode frame i+2 on a low-priority side
-        # stream (own engine = own workspace) while the latency-bound decode / heads / value chain of step i runs on a
-        # high-priority stream, instead of encoding the whole sequence up front.  Same arithmetic per frame.
-        self.overlap_encoder = os.environ.get("S3R_ENC_OVERLAP", "0") == "1"
-        self._enc_engines = {}
-        self._streams = None
         self._packed = None
         self._packed_dirty = True
+        self._packed_moved = False
         self._engines = {}
         self._pos_cache = {}
         if dus3r_name is not None:
@@ -336,6 +331,7 @@ class Spann3R(ParamModule):
 
     def _apply(self, fn, *a, **k):
         self._packed_dirty = True
+        self._packed_moved = True
         return super()._apply(fn, *a, **k)
 
     def _weights(self) -> PackedWeights:
@@ -344,14 +340,30 @@ class Spann3R(ParamModule):
             if dev.type != "cuda":
                 raise RuntimeError("spann3r_b200.Spann3R runs on a B200 only: call .to('cuda') first (no CPU path)")
             self._engines.clear()
-            self._enc_engines.clear()
             self._packed = None
             self._packed = PackedWeights(self.state_dict(), device=dev)
             self._packed_dirty = False
         return self._packed
 
-    def _engine_for(self, B, H, W, n_frames=2, encode_only=False) -> Engine:
-        w = self._weights()
+    def _weights_train(self) -> PackedWeights:
+        """Training: the parameters change every optimizer step, so every forward re-packs them -- with device arithmetic
+        and IN PLACE (`PackedWeights.refresh`), which keeps the engines and their cached tile plans valid."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("spann3r_b200.Spann3R runs on a B200 only: call .to('cuda') first (no CPU path)")
+        sd = self.state_dict()
+        if self._packed is None or self._packed.host_math or self._packed.device != dev or self._packed_moved:
+            self._engines.clear()
+            self._packed = None
+            self._packed = PackedWeights(sd, device=dev, host_math=False)
+            self._packed_moved = False
+        else:
+            self._packed.refresh(sd)
+        self._packed_dirty = True      # a later eval-mode call must re-pack: the optimizer steps after this forward
+        return self._packed
+
+    def _engine_for(self, B, H, W, n_frames=2, encode_only=False, training=False) -> Engine:
+        w = self._weights_train() if training else self._weights()
         max_images = max(2 * B, min(n_frames * B, self.max_encode_batch * B))
         key = (B, H, W)
         eng = self._engines.get(key)
@@ -385,11 +397,18 @@ class Spann3R(ParamModule):
         return self._pos_cache[key].view(1, -1, 2).expand(B, -1, 2).clone()
 
     # -- forward -----------------------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, frames, return_memory=False):
-        """spann3r/model.py:473-539 (eval mode)."""
+        """spann3r/model.py:473-539.  Eval mode: the inference path below.  Training mode (`self.training`): the same CUDA
+        forward with the reference's training branches and a PyTorch-recompute backward (`train.py`)."""
+        if self.training and torch.is_grad_enabled():
+            from .train import forward_train
+            return forward_train(self, frames, return_memory)
         if self.training:
-            raise NotImplementedError("spann3r_b200 implements the inference forward; call .eval() first")
+            raise RuntimeError("Spann3R is in training mode but autograd is disabled: call .eval() for inference")
+        return self._forward_eval(frames, return_memory)
+
+    @torch.no_grad()
+    def _forward_eval(self, frames, return_memory=False):
         F_ = len(frames)
         img0 = frames[0]["img"]
         B, _, H, W = img0.shape
@@ -401,8 +420,6 @@ class Spann3R(ParamModule):
         # The encoder has no dependence on the memory loop: encode every frame up front in large batches
         # (SURVEY.md §3.1); per-image results are identical to the reference's pair / single-frame calls.
         imgs = [self._dev(f["img"]) for f in frames]
-        if self.overlap_encoder and F_ > 2:
-            return self._forward_overlapped(frames, imgs, eng, sp_mem, return_memory)
         feats = []
         chunk = max(1, eng.max_images // B)
         for s in range(0, F_, chunk):
@@ -411,62 +428,8 @@ class Spann3R(ParamModule):
             feats += list(out.view(len(part), B, N, 1024).unbind(0))
         return self._frame_loop(F_, H, W, eng, sp_mem, lambda i: feats[i], return_memory)
 
-    def _forward_overlapped(self, frames, imgs, eng, sp_mem, return_memory):
-        """S3R_ENC_OVERLAP=1 (experiment): frames 0, 1 are encoded on the decode stream; frame i+2 is encoded by a second
-        engine (own workspace, shared weights) on a low-priority stream while step i runs; step i+1 waits on its event."""
-        F_ = len(frames)
-        B, _, H, W = imgs[0].shape
-        N = eng.N
-        key = (B, H, W)
-        enc = self._enc_engines.get(key)
-        if enc is None:
-            enc = self._enc_engines[key] = Engine(self._weights(), B, H, W, max_images=2 * B)
-        if self._streams is None:
-            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
-            self._streams = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=lo))   # (decode chain, encoder)
-        dec_s, enc_s = self._streams
-        caller = torch.cuda.current_stream()
-        dec_s.wait_stream(caller)
-        enc_s.wait_stream(caller)
-        feats, ready = {}, {}
-
-        def enqueue_encode(j):
-            with torch.cuda.stream(enc_s):
-                f = enc.encode(imgs[j])
-                ev = torch.cuda.Event()
-                ev.record(enc_s)
-            f.record_stream(dec_s)
-            feats[j], ready[j] = f, ev
-
-        def feat_of(j):
-            """The frame loop asks for (i, i + 1) at the top of step i: start the NEXT frame's encoder before this step's
-            work is enqueued, then make the decode stream wait for frame j if it came from the side stream."""
-            if j + 1 < F_ and (j + 1) not in feats:
-                enqueue_encode(j + 1)
-            ev = ready.pop(j, None)
-            if ev is not None:
-                dec_s.wait_event(ev)
-            return feats[j]
-
-        with torch.cuda.stream(dec_s):
-            first = eng.encode(torch.cat(imgs[:2], dim=0)).view(2, B, N, 1024)
-            feats[0], feats[1] = first[0], first[1]
-            out = self._frame_loop(F_, H, W, eng, sp_mem, feat_of, return_memory)
-        caller.wait_stream(dec_s)
-        caller.wait_stream(enc_s)
-        for p in out[0]:                         # results were allocated on dec_s and are consumed on the caller's stream
-            for t in p.values():
-                t.record_stream(caller)
-        for _, r2 in out[1]:
-            for t in r2.values():
-                t.record_stream(caller)
-        if sp_mem.bank is not None:
-            for name in ("kn_hi", "kn_lo", "vnt_hi", "vnt_lo", "k_raw", "v_raw", "attn", "count"):
-                getattr(sp_mem.bank, name).record_stream(caller)
-        return out
-
     def _frame_loop(self, F_, H, W, eng, sp_mem, feat_of, return_memory):
-        """The frame loop of spann3r/model.py:484-533 over already (or concurrently) encoded frames."""
+        """The frame loop of spann3r/model.py:484-533 over the already encoded frames."""
         portrait = H > W        # heads run at (H, W); outputs and the value encoder's input are the landscape views
         feat_k2 = None
         preds, preds_all = None, []

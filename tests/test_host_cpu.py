@@ -321,80 +321,6 @@ def test_only_checkers_touch_the_oracle():
     assert pat.search(entry[entry.index("def smoke"):]) and not pat.search(entry[: entry.index("def smoke")])
 
 
-def test_overlapped_encoder_schedule_on_fakes(monkeypatch):
-    """S3R_ENC_OVERLAP experiment (model.py:_forward_overlapped), scheduling logic only: frames 0, 1 are encoded in one call,
-    frame i+2 is enqueued on the encoder stream BEFORE step i's decode and waited for before step i+1 uses it, and the
-    outputs equal the default schedule's.  CUDA streams / events are replaced by recording fakes."""
-    from spann3r_b200 import synth
-    from spann3r_b200 import model as M
-    log = []
-
-    class FakeStream:
-        def __init__(self, priority=0):
-            self.name = f"s{priority}"
-
-        def wait_stream(self, other):
-            log.append(("wait_stream", self.name))
-
-        def wait_event(self, ev):
-            log.append(("wait_event", ev.tag))
-
-        @staticmethod
-        def priority_range():
-            return (0, -1)
-
-    class FakeEvent:
-        def __init__(self):
-            self.tag = None
-
-        def record(self, stream=None):
-            self.tag = log[-1][1] if log and log[-1][0] == "encode" else None
-
-    class Ctx:
-        def __init__(self, s): pass
-        def __enter__(self): return self
-        def __exit__(self, *a): return False
-
-    m, engines = _fake_model(monkeypatch)
-    H, W, F_ = 64, 96, 5
-    frames = synth.make_frames(F_, H, W)
-    base, _ = m(frames)
-    base = [{k: v.clone() for k, v in p.items()} for p in base]
-
-    class LoggingEngine(_FakeEngine):
-        def encode(self, img):
-            log.append(("encode", int(img.shape[0]) * 1000 + len([1 for e in log if e[0] == "encode"])))
-            return super().encode(img)
-
-        def decode(self, f1, f2, want_all=False):
-            log.append(("decode",))
-            return super().decode(f1, f2, want_all)
-
-    engines.clear()
-    engines[(1, H, W)] = LoggingEngine(1, H, W)
-    monkeypatch.setattr(M, "Engine", lambda w, B, H_, W_, max_images=0: LoggingEngine(B, H_, W_))
-    monkeypatch.setattr(m, "_weights", lambda: None)
-    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
-    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: FakeStream(9))
-    monkeypatch.setattr(torch.cuda, "stream", Ctx)
-    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
-    m.overlap_encoder = True
-    log.clear()
-    out, _ = m(frames)
-    for a, b in zip(out, base):
-        assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in b)
-    seq = [e for e in log if e[0] in ("encode", "decode", "wait_event")]
-    kinds = [e[0] for e in seq]
-    # pair encode, then [encode(next), decode] for step 0, then [encode(next), wait(frame), decode] ...
-    assert kinds[:3] == ["encode", "encode", "decode"] and seq[0][1] // 1000 == 2 and seq[1][1] // 1000 == 1
-    assert kinds.count("encode") == 1 + (F_ - 2) and kinds.count("decode") == F_ - 1 and kinds.count("wait_event") == F_ - 2
-    for i in range(1, F_ - 1):                                  # before decode #i: frame i+1 was waited for ...
-        d = [j for j, k in enumerate(kinds) if k == "decode"][i]
-        assert "wait_event" in kinds[:d] and kinds[:d].count("wait_event") == i
-        assert kinds[:d].count("encode") == min(1 + i + 1, 1 + F_ - 2)     # ... and frame i+2's encoder is already enqueued
-
-
 def test_reference_style_init_and_zero_fill(tmp_path, spec):
     """parameters are never uninitialised memory.  Without a DUSt3R checkpoint they are zero-filled (the
     caller loads a full Spann3R state dict); with one, the keys it does not cover get the reference constructors' default

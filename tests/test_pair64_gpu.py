@@ -1,16 +1,12 @@
-"""GPU tests of kernels / variants written after the round's GPU minutes were spent: NOT selected by `-m gpu` (marker
-gpu_unverified), skipped without a GPU.  First call of the next round: `bash tools/gpu_round.sh rN unverified`; what passes
-moves to the regular files with the `gpu` marker.
-
-* 256 x 64 CTA-pair GEMM tiles (`gemm2_bf16x3_kernel<64, *>`, force_bn 2064 / S3R_GEMM2_64=1): same op-level parity bodies
-  as tests/test_ops_gpu.py.
-"""
+"""256 x 64 CTA-pair GEMM tiles (`gemm2_bf16x3_kernel<64, *>`, force_bn 2064 / s3r_set_option("gemm2_64", 1)): the same
+op-level parity bodies as tests/test_ops_gpu.py.  Written without a GPU at the end of round 1, verified on a B200 in the
+first call of round 2 (profiles/r2a_unverified.log)."""
 import pytest
 import torch
 
 import test_ops_gpu as ops
 
-pytestmark = [pytest.mark.gpu_unverified, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a B200")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,42 @@
+#!/bin/bash
+# Round-2 evidence script (one gpurun call, every step under its own timeout).  Usage, from the repo root through gpurun:
+#   gpurun --timeout 2400 -- 'bash tools/gpu_r2.sh r2a unverified tests ab bench ncu'
+# steps: unverified = tests still marked gpu_unverified; tests = full `pytest -m gpu`; ab = in-situ A/B of the switches below
+#        (quick bench legs, same box); bench = full bench.py line (real-reference CPU + eager-GPU legs); ncu = launch list of
+#        one sequence; smoke = __graft_entry__.smoke() under an ncu launch list (what the driver records); multi = 2-GPU tests
+tag=${1:-r2}; shift
+mkdir -p gpurun_out
+quick() {   # quick NAME [ENV=VAL ...]: one short bench leg, prints value / ms / gemm ms
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 8 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-raw 2> gpurun_out/${tag}_ab_${name}.err \
+    | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; print('$name', round(d['value'],1), 'frames/s', round(d['ms_per_step'],2), 'ms  e2e', round(d['e2e']['value'],1), ' gemm', round(r['gemm_ms_per_seq'],2), 'ms attn', round(r['attention_ms_per_seq'],2), 'ms launches', d['gpu_launches'])" \
+    | tee -a gpurun_out/${tag}_ab.txt
+}
+for step in "$@"; do
+  case $step in
+    unverified) timeout 400 python -m pytest tests -q -m gpu_unverified > gpurun_out/${tag}_unverified.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_unverified.log; tail -12 gpurun_out/${tag}_unverified.log ;;
+    tests) timeout 1200 python -m pytest tests -q -m gpu --durations=12 > gpurun_out/${tag}_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_tests.log; tail -30 gpurun_out/${tag}_tests.log ;;
+    ab)    quick base
+           quick prefetch_off S3R_PREFETCH_B=0
+           quick pair64 S3R_GEMM2_64=1
+           quick attn64 S3R_LIB=ab/libspann3r_b200_attn64.so
+           quick overlap S3R_ENC_OVERLAP=1
+           quick base_again ;;
+    bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-1500 gpurun_out/${tag}_bench.json ;;
+    ncu)   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+             --profile-from-start off --csv --log-file gpurun_out/${tag}_launches.csv python tools/profile_seq.py > gpurun_out/${tag}_ncu.log 2>&1
+           python tools/summarize_ncu.py gpurun_out/${tag}_launches.csv --title "${tag}: ncu launch list of ONE 10-frame 512x384 sequence (B=1)" \
+             > gpurun_out/${tag}_launches.md 2>> gpurun_out/${tag}_ncu.log; head -30 gpurun_out/${tag}_launches.md ;;
+    smoke) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file gpurun_out/${tag}_smoke_launches.csv \
+             python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
+           python - <<PY
+import csv, collections
+rows = [r for r in csv.reader(open("gpurun_out/${tag}_smoke_launches.csv")) if len(r) > 5 and r[0].isdigit()]
+c = collections.Counter(r[4].split("(")[0][:70] for r in rows)
+print("first 1000 launches of smoke():", len(rows)); [print(" ", n, k) for k, n in c.most_common(14)]
+PY
+           ;;
+    multi) timeout 600 python -m pytest tests/test_multi_gpu.py -q -m gpu > gpurun_out/${tag}_multi.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_multi.log; tail -8 gpurun_out/${tag}_multi.log ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
