@@ -184,8 +184,9 @@ def _eager_gpu_legs(mref, why, sd, frames_dev, model, dev, F_):
         # the reference caches token positions per (h, w) WITHOUT the device (croco/models/blocks.py:195-207): a model that ran
         # on the CPU first (the cpu_baseline leg) would index with CPU positions on the GPU -- drop the caches, code untouched
         for mod in mref.modules():
-            if hasattr(mod, "cache_positions"):
-                mod.cache_positions = {}
+            pg = getattr(mod, "position_getter", None)      # a plain object hanging off PatchEmbed, not an nn.Module
+            if pg is not None and hasattr(pg, "cache_positions"):
+                pg.cache_positions = {}
         what = "UNMODIFIED reference Spann3R.forward (baseline/_ref), PyTorch eager (cuBLAS/cuDNN), batch 1, same frames"
 
         def fwd(f):

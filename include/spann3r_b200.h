@@ -258,14 +258,14 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
  * softmax output, before the (normally disabled) threshold.  The keep decision of element (b, row, column) is Philox4x32-10
  * of (seed, (b * N + row) * len + column): reproducible, regenerated for the backward pass / tests by s3r_dropout_mask */
 int s3r_engine_memory_read_train(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float drop_p,
-                                 unsigned long long seed, float* out, void* stream);
+                                 uint64_t seed, float* out, void* stream);
 /* Tuning knobs of the tile planner, read when an engine builds its plans (first pass of a stage): "gemm2" (CTA-pair GEMM
  * tiles: 0 off, 1 planner, 128 / 256 forced), "gemm2_64" (256 x 64 pair tiles for the one-wave N = 768 / 1024 GEMMs),
  * "prefetch_b" (weight tiles staged before the programmatic-dependent-launch wait), "attn_pair".  Defaults = the measured
  * best; the call exists so that two engines of one process can be planned differently and timed alternately. */
 int s3r_set_option(const char* name, int value);
 /* out[i] = 0 or 1/(1-p): the keep-scale the training-mode read applies to flat element i = (b * N + row) * len + column */
-int s3r_dropout_mask(float* out, long long n, unsigned long long seed, float p, void* stream);
+int s3r_dropout_mask(float* out, int64_t n, uint64_t seed, float p, void* stream);
 /* spann3r/model.py:80-95 add_mem: append N tokens at bank.len (caller then sets len += N) */
 int s3r_engine_memory_append(s3r_engine* e, const s3r_bank* bank, const float* feat_k, const float* feat_v,
                              void* stream);

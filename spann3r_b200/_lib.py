@@ -56,7 +56,7 @@ _PROTOS = {
     "s3r_gemm_tile_n": (_i, [C.POINTER(GemmDesc)]),
     "s3r_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "s3r_conf_score": (_i, [_vp, _i64, _vp, _vp, _vp]),
-    "s3r_dropout_mask": (_i, [_vp, C.c_longlong, C.c_ulonglong, _f, _vp]),
+    "s3r_dropout_mask": (_i, [_vp, _i64, C.c_uint64, _f, _vp]),
     "s3r_set_option": (_i, [C.c_char_p, _i]),
     "s3r_focal_weiszfeld": (_i, [_vp, _i, _i, _i, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
     "s3r_focal_median": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),

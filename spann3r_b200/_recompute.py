@@ -47,6 +47,13 @@ def _rope(t, cs):
     return torch.cat((rot(y, cy, sy), rot(x, cx, sx)), dim=-1)
 
 
+def _sdpa(q, k, v):
+    """softmax(q k^T / sqrt(dh)) v in plain fp32 ops (not F.scaled_dot_product_attention: which fused backend it picks, and that
+    backend's internal precision, is PyTorch's choice; the backward of a path held to 1e-3 should not depend on it)."""
+    a = torch.softmax((q @ k.transpose(-2, -1)) * (q.shape[-1] ** -0.5), dim=-1)
+    return a @ v
+
+
 def _self_attn(P, n, x, heads, cs):
     """croco/models/blocks.py:94-112."""
     B, N, C = x.shape
@@ -54,7 +61,7 @@ def _self_attn(P, n, x, heads, cs):
     q, k, v = qkv[0], qkv[1], qkv[2]
     if cs is not None:
         q, k = _rope(q, cs), _rope(k, cs)
-    o = F.scaled_dot_product_attention(q, k, v)            # softmax(q k^T / sqrt(dh)) v
+    o = _sdpa(q, k, v)
     return _lin(P, n + ".proj", o.transpose(1, 2).reshape(B, N, C))
 
 
@@ -65,7 +72,7 @@ def _cross_attn(P, n, xq, y, heads, cs):
     q = _lin(P, n + ".projq", xq).view(B, N, heads, dh).transpose(1, 2)
     k = _lin(P, n + ".projk", y).view(B, -1, heads, dh).transpose(1, 2)
     v = _lin(P, n + ".projv", y).view(B, -1, heads, dh).transpose(1, 2)
-    o = F.scaled_dot_product_attention(_rope(q, cs), _rope(k, cs), v)
+    o = _sdpa(_rope(q, cs), _rope(k, cs), v)
     return _lin(P, n + ".proj", o.transpose(1, 2).reshape(B, N, C))
 
 

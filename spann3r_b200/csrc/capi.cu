@@ -186,11 +186,12 @@ int s3r_set_option(const char* name, int value) {
   else if (!strcmp(name, "gemm2_64")) o.gemm2_64 = value;
   else if (!strcmp(name, "prefetch_b")) o.prefetch_b = value;
   else if (!strcmp(name, "attn_pair")) o.attn_pair = value;
-  else { set_error("s3r_set_option: unknown option '%s' (gemm2, gemm2_64, prefetch_b, attn_pair)", name); return -1; }
+  else if (!strcmp(name, "chain")) o.chain = value;
+  else { set_error("s3r_set_option: unknown option '%s' (gemm2, gemm2_64, prefetch_b, attn_pair, chain)", name); return -1; }
   return 0;
 }
 
-int s3r_dropout_mask(float* out, long long n, unsigned long long seed, float p, void* stream) {
+int s3r_dropout_mask(float* out, int64_t n, uint64_t seed, float p, void* stream) {
   if (!out && n > 0) {
     set_error("s3r_dropout_mask: null output");
     return -1;

@@ -60,13 +60,18 @@ struct Epi {
 struct PlanCache {
   std::vector<GemmPlan> gemms;
   std::vector<AttnPlan> attns;
-  size_t gc = 0, ac = 0;
+  std::vector<ChainPlan> chains;   // runs of consecutive GEMM plans launched as ONE persistent kernel (gemm_chain.cu)
+  size_t gc = 0, ac = 0, cc = 0;
   bool building = true;
+  bool chain_open = false, use_chain = false;
+  size_t chain_first = 0;
   void begin() {
-    gc = ac = 0;
+    gc = ac = cc = 0;
+    chain_open = false;
     if (building) {   // a previous first pass failed half way (e.g. a plan_init error): start the plan list over
       gemms.clear();
       attns.clear();
+      chains.clear();
     }
   }
   void end() { building = false; }
@@ -156,6 +161,14 @@ struct s3r_engine {
       int r = gemm_plan_init(&pc.gemms.back(), A.hi, A.lo, Bw.hi, Bw.lo, g.groups, g.NB, g.H, g.W, g.Kc, g.taps, g.N,
                              e.epi == EPI_HEADTAIL ? 1128 : g.force_bn, g.lda, g.ldb, g.b_group_rows);
       if (r) return r;
+      const GemmArgs& pa = pc.gemms.back().args;
+      const bool even_rows = ((pa.tiles_w * pa.tiles_h * pa.NB) & 1) == 0;   // CTA pairs need an even number of 128-row tiles
+      if (pc.chain_open && !pc.gemms.back().two_cta && even_rows) {   // every phase of a chain runs on CTA pairs
+        const int bn = pc.gemms.back().bn;
+        r = gemm_plan_init(&pc.gemms.back(), A.hi, A.lo, Bw.hi, Bw.lo, g.groups, g.NB, g.H, g.W, g.Kc, g.taps, g.N, 2000 + bn,
+                           g.lda, g.ldb, g.b_group_rows);
+        if (r) return r;
+      }
       pc.gemms.back().b_static = (g.b_static && options().prefetch_b) ? 1 : 0;   // decided when the plan is built
     }
     if (pc.gc >= pc.gemms.size()) {
@@ -183,11 +196,81 @@ struct s3r_engine {
     a.stats_out = e.stats_out;
     a.b_static = p.b_static;
     flops += p.flops;
+    if (pc.chain_open) return 0;   // launched by chain_end() together with the other phases
     ++launches;
     if (!profiling) return gemm_launch(p, st);
     Timed t; t.a = get_event(); t.b = get_event(); t.flops = p.flops; t.kind = 0;
     cudaEventRecord(t.a, st);
     int r = gemm_launch(p, st);
+    cudaEventRecord(t.b, st);
+    timed.push_back(t);
+    return r;
+  }
+
+  // The GEMM calls between chain_begin() and chain_end() are dependent linear layers on the same rows (phase p+1 consumes
+  // what phase p writes): they become ONE persistent launch with per-row-block dependency counters (gemm_chain.cu).
+  void chain_begin(PlanCache& pc) {
+    if (pc.building) pc.use_chain = options().chain != 0;   // decided when the plans are built, replayed as built
+    if (!pc.use_chain) return;
+    pc.chain_open = true;
+    pc.chain_first = pc.gc;
+  }
+  int chain_end(PlanCache& pc, cudaStream_t st) {
+    if (!pc.chain_open) return 0;
+    pc.chain_open = false;
+    const int n = (int)(pc.gc - pc.chain_first);
+    if (n == 0) return 0;
+    if (pc.building) {
+      const GemmPlan* items[kChainMaxPhases] = {};
+      if (n > kChainMaxPhases) {
+        set_error("engine: chain of %d phases", n);
+        return -8;
+      }
+      bool pairs = true;
+      for (int i = 0; i < n; ++i) {
+        items[i] = &pc.gemms[pc.chain_first + i];
+        pairs = pairs && items[i]->two_cta;
+      }
+      pc.chains.emplace_back();
+      if (pairs) {
+        const int cap = 1 + n * items[0]->args.groups * items[0]->args.tiles_w * items[0]->args.tiles_h * items[0]->args.NB;
+        uint32_t* dct = alloc<uint32_t>(cap);
+        if (status) return status;
+        int r = chain_plan_init(&pc.chains.back(), items, n, dct, cap);
+        if (r) return r;
+      } else {   // an odd number of 128-row tiles (e.g. 4 x 196 tokens): no CTA pairs, the run goes out as separate launches
+        memset(&pc.chains.back(), 0, sizeof(ChainPlan));
+        pc.chains.back().first = (int)pc.chain_first;
+        pc.chains.back().count = n;
+      }
+    }
+    if (pc.cc >= pc.chains.size()) {
+      set_error("engine: chain plan cache out of sync");
+      return -8;
+    }
+    const ChainPlan& cp = pc.chains[pc.cc++];
+    if (cp.count > 0) {
+      for (int i = 0; i < cp.count; ++i) {
+        const GemmPlan& p = pc.gemms[cp.first + i];
+        ++launches;
+        if (!profiling) {
+          if (int r = gemm_launch(p, st)) return r;
+          continue;
+        }
+        Timed t; t.a = get_event(); t.b = get_event(); t.flops = p.flops; t.kind = 0;
+        cudaEventRecord(t.a, st);
+        int r = gemm_launch(p, st);
+        cudaEventRecord(t.b, st);
+        timed.push_back(t);
+        if (r) return r;
+      }
+      return 0;
+    }
+    ++launches;
+    if (!profiling) return chain_launch(cp, st);
+    Timed t; t.a = get_event(); t.b = get_event(); t.flops = cp.flops; t.kind = 0;
+    cudaEventRecord(t.a, st);
+    int r = chain_launch(cp, st);
     cudaEventRecord(t.b, st);
     timed.push_back(t);
     return r;
@@ -223,41 +306,50 @@ struct s3r_engine {
                             swap, st);
   }
 
-  // ---- one ViT block on X [nimg*N, D] (in place).  croco/models/blocks.py:127-130 ----
-  // LayerNorms are folded into the GEMM that consumes them (s3r_lin.cs): on entry P holds the planes of the block
-  // input x and St1 its per-row chunk statistics (written by whichever GEMM produced x); on exit likewise for
-  // the block output.  No LayerNorm kernel runs inside a block.
-  int vit_block(PlanCache& pc, const s3r_block_w& bw, int D, int nimg, bool rope, float* Xp, cudaStream_t st,
-                const int* pos_tab = nullptr) {
+  // ---- ViT blocks on X [nimg*N, D] (in place).  croco/models/blocks.py:127-130 ----
+  // LayerNorms are folded into the GEMM that consumes them (s3r_lin.cs): P holds the planes of the block input x and St1
+  // its per-row chunk statistics (written by whichever GEMM produced x).  No LayerNorm kernel runs inside a block.
+  // Launch structure per block: [qkv of block 0] then, per block, attention + ONE chain launch (proj -> fc1 -> fc2 -> the
+  // NEXT block's qkv); without the chain option the same GEMMs go out one by one.
+  int vit_qkv(PlanCache& pc, const s3r_block_w& bw, int D, int nimg, bool rope, cudaStream_t st, const int* pos_tab) {
+    const int rows = nimg * N;
+    Geom g; g.W = rows; g.Kc = D; g.N = 3 * D;
+    Epi e; e.epi = EPI_QKV; e.bias = bw.qkv.b; e.q_C = D; e.q_role_base = 0; e.q_ntok = N; e.q_ntok_pad = Npad;
+    e.q_rope = rope ? 1 : 0; e.q_nb = nimg; e.q_pos = pos_tab; e.q_cs = (const float2*)w.rope_cs;
+    e.q_out = Qb; e.k_out = Kb; e.vt_out = Vtb; e.q_scale = 0.125f;
+    e.ln_stats = St1; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.qkv.cs;                       // norm1
+    return gemm(pc, P, WP(bw.qkv.w), g, e, st);
+  }
+  int vit_blocks(PlanCache& pc, const s3r_block_w* blocks, int depth, int D, int nimg, bool rope, float* Xp, cudaStream_t st,
+                 const int* pos_tab = nullptr) {
     const int rows = nimg * N, heads = D / 64;
     if (!pos_tab) pos_tab = pos;
     int r;
-    {
-      Geom g; g.W = rows; g.Kc = D; g.N = 3 * D;
-      Epi e; e.epi = EPI_QKV; e.bias = bw.qkv.b; e.q_C = D; e.q_role_base = 0; e.q_ntok = N; e.q_ntok_pad = Npad;
-      e.q_rope = rope ? 1 : 0; e.q_nb = nimg; e.q_pos = pos_tab; e.q_cs = (const float2*)w.rope_cs;
-      e.q_out = Qb; e.k_out = Kb; e.vt_out = Vtb; e.q_scale = 0.125f;
-      e.ln_stats = St1; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.qkv.cs;                       // norm1
-      if ((r = gemm(pc, P, WP(bw.qkv.w), g, e, st))) return r;
-    }
-    if ((r = attention(pc, Qb, Kb, Vtb, nimg * heads, heads, N, N, AO, D, st))) return r;
-    {
-      Geom g; g.W = rows; g.Kc = D; g.N = D;
-      Epi e; e.bias = bw.proj.b; e.res1 = Xp; e.ldr1 = D; e.out = Xp; e.ldo = D;
-      e.op = P2; e.ldp = D; e.stats_out = St2;
-      if ((r = gemm(pc, AO, WP(bw.proj.w), g, e, st))) return r;
-    }
-    {
-      Geom g; g.W = rows; g.Kc = D; g.N = 4 * D;
-      Epi e; e.bias = bw.fc1.b; e.act = ACT_GELU; e.op = Hb; e.ldp = 4 * D;
-      e.ln_stats = St2; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.fc1.cs;                       // norm2
-      if ((r = gemm(pc, P2, WP(bw.fc1.w), g, e, st))) return r;
-    }
-    {
-      Geom g; g.W = rows; g.Kc = 4 * D; g.N = D;
-      Epi e; e.bias = bw.fc2.b; e.res1 = Xp; e.ldr1 = D; e.out = Xp; e.ldo = D;
-      e.op = P; e.ldp = D; e.stats_out = St1;
-      if ((r = gemm(pc, Hb, WP(bw.fc2.w), g, e, st))) return r;
+    if ((r = vit_qkv(pc, blocks[0], D, nimg, rope, st, pos_tab))) return r;
+    for (int l = 0; l < depth; ++l) {
+      const s3r_block_w& bw = blocks[l];
+      if ((r = attention(pc, Qb, Kb, Vtb, nimg * heads, heads, N, N, AO, D, st))) return r;
+      chain_begin(pc);
+      {
+        Geom g; g.W = rows; g.Kc = D; g.N = D;
+        Epi e; e.bias = bw.proj.b; e.res1 = Xp; e.ldr1 = D; e.out = Xp; e.ldo = D;
+        e.op = P2; e.ldp = D; e.stats_out = St2;
+        if ((r = gemm(pc, AO, WP(bw.proj.w), g, e, st))) return r;
+      }
+      {
+        Geom g; g.W = rows; g.Kc = D; g.N = 4 * D;
+        Epi e; e.bias = bw.fc1.b; e.act = ACT_GELU; e.op = Hb; e.ldp = 4 * D;
+        e.ln_stats = St2; e.ln_np = D / 32; e.ln_eps = 1e-6f; e.ln_cs = bw.fc1.cs;                       // norm2
+        if ((r = gemm(pc, P2, WP(bw.fc1.w), g, e, st))) return r;
+      }
+      {
+        Geom g; g.W = rows; g.Kc = 4 * D; g.N = D;
+        Epi e; e.bias = bw.fc2.b; e.res1 = Xp; e.ldr1 = D; e.out = Xp; e.ldo = D;
+        e.op = P; e.ldp = D; e.stats_out = St1;
+        if ((r = gemm(pc, Hb, WP(bw.fc2.w), g, e, st))) return r;
+      }
+      if (l + 1 < depth && (r = vit_qkv(pc, blocks[l + 1], D, nimg, rope, st, pos_tab))) return r;
+      if ((r = chain_end(pc, st))) return r;
     }
     return 0;
   }
@@ -501,8 +593,7 @@ int s3r_engine_encode(s3r_engine* e, const float* img, int nimg, float* feat, vo
     ep.op = e->P; ep.ldp = 1024; ep.stats_out = e->St1;   // block 0's folded norm1 reads these
     if ((r = e->gemm(pc, e->Pim, WP(e->w.patch_embed.w), g, ep, st))) return r;
   }
-  for (int l = 0; l < 24; ++l)
-    if ((r = e->vit_block(pc, e->w.enc[l], 1024, nimg, true, e->X, st))) return r;
+  if ((r = e->vit_blocks(pc, e->w.enc, 24, 1024, nimg, true, e->X, st))) return r;
   if ((r = e->ln(e->X, e->w.enc_norm, 0, 0, 1e-6f, rows, 1024, feat, 1024, Planes(), 0, 0, 0, st))) return r;
   pc.end();
   return 0;
@@ -535,20 +626,25 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
   // of the layer input (both streams), Sa its chunk statistics: read by qkv (norm1) and -- with the groups swapped,
   // each stream cross-attends to the OTHER stream's layer input -- by kv (norm_y).  Pb / Sb: x after self attention
   // (norm2 -> q), Pc / Sc: x after cross attention (norm3 -> fc1).  fc2 writes the next layer's xin / Sa.
-  Planes xin = e->Pa;
-  for (int l = 0; l < 12; ++l) {
-    const s3r_decblock_w& bw = e->w.dec[l];
+  // Launch structure: [qkv of layer 0], then per layer: self attention, chain (proj -> q), cross attention, chain (cproj ->
+  // fc1 -> fc2 -> the NEXT layer's qkv): 4 launches per layer instead of 9 (the same GEMMs one by one without the chain option).
+  auto qkv_launch = [&](int l, Planes xin) {
     // self-attention q, k, v (norm1 folded) and -- same launch, columns >= 2304 reading the OTHER stream's layer
     // input (norm_y folded, group swap) -- the cross-attention k, v
-    {
-      Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 3840;
-      Epi ep; ep.epi = EPI_QKV; ep.bias = bw.qkv.b; ep.q_C = 768; ep.q_role_base = 0; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
-      ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
-      ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.k2_out = e->Kd2; ep.vt2_out = e->Vtd2; ep.q_scale = 0.125f;
-      ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.qkv.cs; ep.a_swap = 1; ep.swap_col0 = 2304;
-      if ((r = e->gemm(pc, xin, WP(bw.qkv.w), g, ep, st))) return r;
-    }
+    const s3r_decblock_w& bw = e->w.dec[l];
+    Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 3840;
+    Epi ep; ep.epi = EPI_QKV; ep.bias = bw.qkv.b; ep.q_C = 768; ep.q_role_base = 0; ep.q_ntok = N; ep.q_ntok_pad = e->Npad;
+    ep.q_rope = 1; ep.q_nb = B; ep.q_pos = e->pos; ep.q_cs = cs;
+    ep.q_out = e->Qd; ep.k_out = e->Kd; ep.vt_out = e->Vtd; ep.k2_out = e->Kd2; ep.vt2_out = e->Vtd2; ep.q_scale = 0.125f;
+    ep.ln_stats = e->Sa; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.qkv.cs; ep.a_swap = 1; ep.swap_col0 = 2304;
+    return e->gemm(pc, xin, WP(bw.qkv.w), g, ep, st);
+  };
+  Planes xin = e->Pa;
+  if ((r = qkv_launch(0, xin))) return r;
+  for (int l = 0; l < 12; ++l) {
+    const s3r_decblock_w& bw = e->w.dec[l];
     if ((r = e->attention(pc, e->Qd, e->Kd, e->Vtd, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
+    e->chain_begin(pc);
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 768;
       Epi ep; ep.bias = bw.proj.b; ep.res1 = e->Xd; ep.ldr1 = 768; ep.out = e->Xd; ep.ldo = 768;
@@ -564,7 +660,9 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
       ep.ln_stats = e->Sb; ep.ln_np = 24; ep.ln_eps = 1e-6f; ep.ln_cs = bw.q.cs;                        // norm2
       if ((r = e->gemm(pc, e->Pb, WP(bw.q.w), g, ep, st))) return r;
     }
+    if ((r = e->chain_end(pc, st))) return r;
     if ((r = e->attention(pc, e->Qd, e->Kd2, e->Vtd2, 2 * B * 12, 12, N, N, e->AOd, 768, st))) return r;
+    e->chain_begin(pc);
     {
       Geom g; g.groups = 2; g.W = (int)R; g.Kc = 768; g.N = 768;
       Epi ep; ep.bias = bw.cproj.b; ep.res1 = e->Xd; ep.ldr1 = 768; ep.out = e->Xd; ep.ldo = 768;
@@ -588,6 +686,8 @@ int s3r_engine_decode(s3r_engine* e, const float* f1, const float* f2, float* de
       if ((r = e->gemm(pc, e->Hd, WP(bw.fc2.w), g, ep, st))) return r;
       xin = xout;
     }
+    if (l < 11 && (r = qkv_launch(l + 1, xin))) return r;
+    if ((r = e->chain_end(pc, st))) return r;
     if (dec_all && l < 11) {
       ++e->launches;
       cudaMemcpyAsync(dec_all + (size_t)l * 2 * R * 768, e->Xd, (size_t)2 * R * 768 * sizeof(float),
@@ -781,8 +881,7 @@ int s3r_engine_value(s3r_engine* e, const float* pts3d, const float* feat_k1, in
     ep.op = e->P; ep.ldp = 1024; ep.stats_out = e->St1;
     if ((r = e->gemm(pc, e->Pim, WP(e->w.pos_patch_embed.w), g, ep, st))) return r;
   }
-  for (int l = 0; l < 6; ++l)
-    if ((r = e->vit_block(pc, e->w.val[l], 1024, B, rope, e->Xv, st, tr ? e->pos_t : e->pos))) return r;
+  if ((r = e->vit_blocks(pc, e->w.val, 6, 1024, B, rope, e->Xv, st, tr ? e->pos_t : e->pos))) return r;
   if ((r = e->ln(e->Xv, e->w.value_norm, 0, 0, 1e-6f, rows, 1024, nullptr, 0, e->Pv, 1024, 0, 0, st))) return r;
   {
     Geom g; g.W = rows; g.Kc = 1024; g.N = 1024;
@@ -804,7 +903,7 @@ int s3r_engine_memory_read(s3r_engine* e, const s3r_bank* bank, const float* fea
 // training-mode read (spann3r/model.py:474 attn_thresh = 0, :167-168 dropout on the attention weights): same launches, the
 // softmax stage additionally applies the Philox keep-scale of (seed, row * M + column)
 int s3r_engine_memory_read_train(s3r_engine* e, const s3r_bank* bank, const float* feat, float thresh, float drop_p,
-                                 unsigned long long seed, float* out, void* stream) {
+                                 uint64_t seed, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   S3R_ENGINE_DEVICE(e, "s3r_engine_memory_read");
   if (!(drop_p >= 0.f && drop_p < 1.f)) {

@@ -387,6 +387,7 @@ Options& options() {
     if (const char* e = getenv("S3R_GEMM2_64")) x.gemm2_64 = atoi(e);
     if (const char* e = getenv("S3R_PREFETCH_B")) x.prefetch_b = atoi(e);
     if (const char* e = getenv("S3R_ATTN_PAIR")) x.attn_pair = atoi(e);
+    if (const char* e = getenv("S3R_CHAIN")) x.chain = atoi(e);
     return x;
   }();
   return o;

@@ -94,12 +94,39 @@ int gemm2_launch(const GemmPlan& plan, cudaStream_t stream);   // 2-CTA kernel (
 // process can be planned under different settings and timed alternately (tools/ab_inproc.py).
 struct Options {
   int gemm2 = 1;        // CTA-pair GEMM tiles: 0 off, 1 planner's choice, 128 / 256 forced width
-  int gemm2_64 = 0;     // 256 x 64 pair tiles where the planner picks 1-CTA 128 x 64 (N = 768 / 1024 GEMMs at B = 1)
+  int gemm2_64 = 1;     // 256 x 64 pair tiles where the planner picks 1-CTA 128 x 64 (N = 768 / 1024 GEMMs at B = 1): each SM
+                        // stages half of B.  In-process A/B on a B200: -1.8 % per sequence (profiles/r2b_ab_inproc.jsonl)
   int prefetch_b = 1;   // stage the first weight tiles before griddepcontrol.wait
   int attn_pair = 1;    // two query tiles per CTA for many-wave attention launches
+  int chain = 1;        // dependent GEMM runs of a block (proj -> fc1 -> fc2 -> next qkv, ...) as one persistent launch
 };
 Options& options();
 int num_sms();
+
+// ---- persistent chain of dependent GEMMs in one launch (gemm_chain.cu) ----
+constexpr int kChainMaxPhases = 4;
+struct ChainPhase {      // one entry of the device-resident phase table
+  GemmArgs args;         // as the standalone launch would get them (tensor maps + fused epilogue)
+  int bn;                // tile width of this phase: 64 / 128 / 256 (always CTA pairs, 256 rows)
+  int dep;               // phase whose 128-row blocks feed this phase's A rows / statistics / residual (-1: inputs of the launch)
+  int dep_need;          // completions per row block of that phase = its n-tile count
+  int ctr_base;          // first counter of this phase: counters[ctr_base + group * m_tiles + m_tile]
+};
+struct ChainParams {     // the kernel's single __grid_constant__ parameter (3.9 KB of the 4 KB parameter space)
+  ChainPhase ph[kChainMaxPhases];
+  uint32_t* ctr;         // device; [0] = ticket of finished CTAs, then the per-(phase, group, row block) counters
+  int nph, n_ctr, bn_max, pad;
+};
+struct ChainPlan {
+  ChainParams params;
+  dim3 grid;
+  double flops;
+  int first, count;      // count > 0: NOT chainable (e.g. an odd number of row tiles): launch gemms[first .. first+count) one by one
+};
+// plans[p]: two-CTA linear-layer plans with EPI_PLAIN / EPI_QKV epilogues and identical row tiling, phase p+1 consuming the
+// rows phase p writes.  dev_counters: counters_cap uint32 (zeroed here).
+int chain_plan_init(ChainPlan* cp, const GemmPlan* const* plans, int nph, uint32_t* dev_counters, int counters_cap);
+int chain_launch(const ChainPlan& cp, cudaStream_t stream);
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box);

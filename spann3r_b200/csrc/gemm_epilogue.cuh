@@ -26,6 +26,14 @@ struct Stg {
   static constexpr int NPASS = 32 / SW;       // passes per 32-column chunk
 };
 
+// Global loads of data another CTA of the SAME launch may have written (chain kernel, gemm_chain.cu: LayerNorm statistics and
+// residual rows produced by an earlier phase): CG = true reads through L2 (ld.global.cg), never a stale L1 line.
+template <bool CG>
+__device__ __forceinline__ float4 ld_f4(const float* p) {
+  if constexpr (CG) return __ldcg(reinterpret_cast<const float4*>(p));
+  else return *reinterpret_cast<const float4*>(p);
+}
+
 __device__ __forceinline__ void apply_act(float (&v)[32], int act) {
   if (act == ACT_GELU) {
 #pragma unroll
@@ -55,6 +63,22 @@ __device__ __forceinline__ void epi_stage_cols(const GemmArgs& args, float* sb, 
       if (args.bias != nullptr)
         b = __ldg(args.bias + ((EPI == EPI_PIXSHUF) ? (long long)g * args.ps_cout + (col % args.ps_cout)
                                                     : (long long)g * args.N + col));
+      if (args.ln_cs != nullptr) c = __ldg(args.ln_cs + (long long)g * args.N + col);
+    }
+    sb[j] = b;
+    scs[j] = c;
+  }
+}
+
+// Same with the tile width as a runtime value (chain kernel: the width changes from phase to phase).
+template <int EPI>
+__device__ __forceinline__ void epi_stage_cols_rt(const GemmArgs& args, float* sb, float* scs, int g, int nt, int bn,
+                                                  int tid_e, int nthr_e) {
+  for (int j = tid_e; j < bn; j += nthr_e) {
+    const int col = nt * bn + j;
+    float b = 0.f, c = 0.f;
+    if (col < args.N) {
+      if (args.bias != nullptr) b = __ldg(args.bias + (long long)g * args.N + col);
       if (args.ln_cs != nullptr) c = __ldg(args.ln_cs + (long long)g * args.N + col);
     }
     sb[j] = b;
@@ -98,7 +122,7 @@ struct EpiTRows {
 // the main loop.  LayerNorm statistics: (sum, sum of squares) per 32-column chunk of the A row, ln_np <= 32 chunks,
 // read cooperatively -- 16 lanes take one row's chunk pairs as float4 (one coalesced 256-byte read per row instead
 // of 16 strided 16-byte reads per thread), two rows per iteration, fixed reduction order.
-template <int EPI, int SW>
+template <int EPI, int SW, bool CG = false>
 __device__ __forceinline__ void epi_tile_pre(const GemmArgs& args, const TileGeom& tg, int quad, int lane, EpiRow& er,
                                              EpiTRows& tr) {
   using S = Stg<SW>;
@@ -119,7 +143,7 @@ __device__ __forceinline__ void epi_tile_pre(const GemmArgs& args, const TileGeo
       const bool v2 = row_pixel(args, tg, rr, h2, w2, pix2);
       t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (v2 && sub < np2)
-        t[i] = reinterpret_cast<const float4*>(args.ln_stats + ((long long)ga * args.out_group_rows + pix2) * args.ln_np)[sub];
+        t[i] = ld_f4<CG>(reinterpret_cast<const float*>(args.ln_stats + ((long long)ga * args.out_group_rows + pix2) * args.ln_np) + 4 * sub);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -172,7 +196,7 @@ __device__ __forceinline__ void epi_tile_pre(const GemmArgs& args, const TileGeo
 }
 
 // Residual values of one 32-column chunk in the transposed layout (EPI_PLAIN; requested one chunk ahead).
-template <int EPI, int SW>
+template <int EPI, int SW, bool CG = false>
 __device__ __forceinline__ void epi_prefetch_res(const GemmArgs& args, const EpiTRows& tr, float4 (&rp)[8], int col0,
                                                  int lane) {
   using S = Stg<SW>;
@@ -184,14 +208,14 @@ __device__ __forceinline__ void epi_prefetch_res(const GemmArgs& args, const Epi
 #pragma unroll
         for (int it = 0; it < S::NIT; ++it)
           if (tr.key[it] >= 0)
-            rp[p * S::NIT + it] = *reinterpret_cast<const float4*>(args.res1 + tr.key[it] * args.ldr1 + col0 + p * SW + cq);
+            rp[p * S::NIT + it] = ld_f4<CG>(args.res1 + tr.key[it] * args.ldr1 + col0 + p * SW + cq);
     }
   }
 }
 
 // One 32-column chunk.  v: this thread's accumulator row; sb / scs: the chunk's staged bias / colsum values; stg: the
 // warp's staging tile; rp: prefetched residual (transposed layout); ht_acc: running dot products of EPI_HEADTAIL.
-template <int EPI, int SW>
+template <int EPI, int SW, bool CG = false>
 __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], const float* sb, const float* scs,
                                           float* stg, const TileGeom& tg, const EpiRow& er, const EpiTRows& tr,
                                           const float4 (&rp)[8], int col0, int lane, float (&ht_acc)[4]) {
@@ -332,11 +356,11 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& args, float (&v)[32], 
           if (args.res1 != nullptr) {
             float4 t;
             if constexpr (EPI == EPI_PLAIN) t = rp[p * S::NIT + it];
-            else t = *reinterpret_cast<const float4*>(args.res1 + orow * args.ldr1 + ocol);
+            else t = ld_f4<CG>(args.res1 + orow * args.ldr1 + ocol);
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
           }
           if (args.res2 != nullptr) {
-            const float4 t = *reinterpret_cast<const float4*>(args.res2 + orow * args.ldr2 + ocol);
+            const float4 t = ld_f4<CG>(args.res2 + orow * args.ldr2 + ocol);
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
           }
         }

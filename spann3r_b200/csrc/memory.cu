@@ -41,8 +41,8 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned
   return u >= p ? keep_scale : 0.f;
 }
 
-__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, unsigned long long seed, float p) {
-  const float ks = 1.0f / (1.0f - p);
+// keep-scale 1 / (1 - p) is evaluated on the host in double and rounded once, as torch.nn.functional.dropout does
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, unsigned long long seed, float p, float ks) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = dropout_scale(seed, (unsigned long long)i, p, ks);
 }
@@ -50,7 +50,7 @@ __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, unsign
 __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restrict__ S, long long ldS, int M, int Mpad,
                                                           float scale, float thresh, __nv_bfloat16* __restrict__ phi,
                                                           __nv_bfloat16* __restrict__ plo, long long ldP, float drop_p,
-                                                          unsigned long long seed) {
+                                                          float keep_scale, unsigned long long seed) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float row[];
@@ -87,7 +87,6 @@ __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restric
   }
   sum = block_reduce(sum, false);
   const float inv = 1.0f / sum;
-  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   float sum2 = 0.f;
   for (int i = tid; i < M; i += 256) {
     float a = row[i] * inv;
@@ -121,7 +120,8 @@ int launch_dropout_mask(float* out, long long n, unsigned long long seed, float 
     return -1;
   }
   const long long blocks = (n + 255) / 256;
-  dropout_mask_kernel<<<(unsigned)(blocks < 2048 ? blocks : 2048), 256, 0, st>>>(out, n, seed, p);
+  dropout_mask_kernel<<<(unsigned)(blocks < 2048 ? blocks : 2048), 256, 0, st>>>(out, n, seed, p,
+                                                                                  (float)(1.0 / (1.0 - (double)p)));
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 
@@ -140,7 +140,7 @@ int launch_mem_softmax(const float* S, long long ldS, long long rows, int M, int
     once.cur() = true;
   }
   launch_pdl(mem_softmax_kernel, dim3((unsigned)rows), dim3(256), smem, st, S, ldS, M, Mpad, scale, thresh, phi, plo, ldP,
-             drop_p, seed);
+             drop_p, (float)(1.0 / (1.0 - (double)drop_p)), seed);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }
 

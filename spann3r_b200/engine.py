@@ -77,7 +77,7 @@ _lib.register_protos({
     "s3r_engine_heads": (_i, [_vp, _vp, _vp, _vp]),
     "s3r_engine_value": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "s3r_engine_memory_read": (_i, [_vp, C.POINTER(Bank), _vp, _f, _vp, _vp]),
-    "s3r_engine_memory_read_train": (_i, [_vp, C.POINTER(Bank), _vp, _f, _f, C.c_ulonglong, _vp, _vp]),
+    "s3r_engine_memory_read_train": (_i, [_vp, C.POINTER(Bank), _vp, _f, _f, C.c_uint64, _vp, _vp]),
     "s3r_engine_memory_append": (_i, [_vp, C.POINTER(Bank), _vp, _vp, _vp]),
     "s3r_engine_check_sim": (_i, [_vp, C.POINTER(Bank), _vp, _i, _vp, _vp]),
     "s3r_engine_take_flops": (C.c_double, [_vp]),

@@ -132,3 +132,85 @@ def test_philox_host_restatement_statistics():
         ctr = [(p1 >> np.uint64(32)) ^ ctr[1] ^ k0, p1 & MASK, (p0 >> np.uint64(32)) ^ ctr[3] ^ k1, p0 & MASK]
         k0, k1 = (k0 + np.uint64(0x9E3779B9)) & MASK, (k1 + np.uint64(0xBB67AE85)) & MASK
     assert [int(v[0]) for v in ctr] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+class _TorchEngine:
+    """Stand-in for engine.Engine on the CPU: every 'native' stage evaluates the recompute restatement (no graph, like the CUDA
+    library), so `train.forward_train` + `train._Stage` run end to end without a GPU."""
+
+    def __init__(self, sd, B, H, W):
+        self.P, self.B, self.H, self.W = sd, B, H, W
+        self.N = (H // 16) * (W // 16)
+        self.max_images, self.device = 16, torch.device("cpu")
+        self.bank_k, self.bank_v = [], []
+
+    def encode(self, img):
+        return R.encode(self.P, img)
+
+    def decode(self, f_fuse, f2, want_all=False):
+        self._dec_in = (f_fuse, f2)
+
+    def keyheads(self, f1, f2):
+        k1, k2, self._pts, self._conf = R.step(self.P, self._dec_in[0], f1, self._dec_in[1], self.H, self.W)
+        return k1, k2
+
+    def heads(self):
+        return self._pts, self._conf
+
+    def value(self, pts3d, k1, transposed=False, rope=False):
+        return R.value(self.P, pts3d, k1, rope)
+
+    def memory_append(self, bank, k, v):
+        self.bank_k.append(k)
+        self.bank_v.append(v)
+        bank.len += self.N
+
+    def memory_read(self, bank, feat, thresh, drop_p=0.0, seed=0):
+        assert thresh == 0.0 and drop_p == 0.0
+        return R.memory_read(self.P, feat, torch.cat(self.bank_k, 1), torch.cat(self.bank_v, 1))
+
+
+def test_training_forward_and_recompute_backward_end_to_end_on_cpu(monkeypatch, sd):
+    """`train.forward_train` (the real frame loop, stage Functions and parameter routing) over a torch stand-in engine:
+    outputs equal the oracle's training-branch forward and the gradients equal autograd through the oracle to fp32 rounding.
+    (On the GPU the same backward is fed by the CUDA forward, whose activations differ by <= 3e-4: tests/test_train_gpu.py.)"""
+    from spann3r_b200 import Spann3R
+    import spann3r_b200.engine as E
+
+    class _Bank:
+        def __init__(self, batch, cap, device):
+            self.len, self.cap = 0, cap
+    monkeypatch.setattr(E, "MemoryBank", _Bank)
+    m = Spann3R(dus3r_name=None, memory_dropout=0.0)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    P = dict(m.named_parameters(remove_duplicate=False))
+    eng = _TorchEngine({k: v.detach() for k, v in P.items()}, 1, H, W)
+    monkeypatch.setattr(m, "_engine_for", lambda *a, **k: eng)
+    monkeypatch.setattr(m, "_dev", lambda t: t)
+    frames = synth.make_frames(3, H, W)
+    g = torch.Generator().manual_seed(5)
+    wts = [torch.randn(1, H, W, 3, generator=g) for _ in range(3)]
+
+    def loss_of(preds):
+        tot = 0.0
+        for p, w in zip(preds, wts):
+            k = "pts3d" if "pts3d" in p else "pts3d_in_other_view"
+            tot = tot + (p[k] * w).sum() + 0.1 * p["conf"].log().sum()
+        return tot
+
+    watch = ["dust3r.enc_blocks.3.attn.qkv.weight", "dust3r.dec_blocks.7.cross_attn.projk.weight", "attn_head_2.0.weight",
+             "norm_k.weight", "value_encoder.4.mlp.fc2.weight", "value_out.bias",
+             "dust3r.downstream_head1.dpt.scratch.refinenet2.resConfUnit1.conv1.weight", "pos_patch_embed.proj.weight"]
+    preds, _ = m(frames)
+    loss = loss_of(preds)
+    loss.backward()
+    got = {k: P[k].grad.clone() for k in watch}
+    sdr = {k: v.clone().requires_grad_(k in watch) for k, v in sd.items()}
+    ref, _ = orc.forward.__wrapped__(sdr, frames, attn_thresh=0, sim_thresh=1.0)
+    for p, r in zip(preds, ref):
+        for k in r:
+            assert rel_l2(p[k].detach(), r[k].detach()) < 1e-5, k
+    grads = torch.autograd.grad(loss_of(ref), [sdr[k] for k in watch])
+    errs = {k: rel_l2(got[k], gr) for k, gr in zip(watch, grads)}
+    assert max(errs.values()) < 2e-4, errs

@@ -19,9 +19,27 @@ for step in "$@"; do
     ab)    quick base
            quick prefetch_off S3R_PREFETCH_B=0
            quick pair64 S3R_GEMM2_64=1
-           quick attn64 S3R_LIB=ab/libspann3r_b200_attn64.so
-           quick overlap S3R_ENC_OVERLAP=1
            quick base_again ;;
+    abin)  timeout 600 python tools/ab_inproc.py gemm2_64=0,1 prefetch_b=0,1 attn_pair=0,1 --rounds 12 > gpurun_out/${tag}_ab_inproc.jsonl 2> gpurun_out/${tag}_ab_inproc.err
+           cat gpurun_out/${tag}_ab_inproc.jsonl; tail -2 gpurun_out/${tag}_ab_inproc.err ;;
+    chain) timeout 600 python -m pytest tests/test_chain_gpu.py -q -m gpu -x -s > gpurun_out/${tag}_chain_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_chain_tests.log; tail -30 gpurun_out/${tag}_chain_tests.log | cut -c1-400 ;;
+    stages) for c in 0 1; do echo "S3R_CHAIN=$c"; S3R_CHAIN=$c timeout 300 python tools/stage_times.py 2>/dev/null | tee -a gpurun_out/${tag}_stage_times_chain$c.json; done ;;
+    abchain) timeout 600 python tools/ab_inproc.py chain=0,1 --rounds 12 > gpurun_out/${tag}_ab_chain.jsonl 2> gpurun_out/${tag}_ab_chain.err; cat gpurun_out/${tag}_ab_chain.jsonl; tail -2 gpurun_out/${tag}_ab_chain.err ;;
+    train) timeout 900 python -m pytest tests/test_train_gpu.py tests/test_model_gpu.py -q -m gpu -k "train or raw or dropout or backward" -s > gpurun_out/${tag}_train_tests.log 2>&1
+           echo "pytest exit $?" >> gpurun_out/${tag}_train_tests.log; tail -25 gpurun_out/${tag}_train_tests.log ;;
+    trainbench) # config 5 on the GPUs of this call (N = CUDA device count): ours, then the reference, NCCL algorithm from its log
+           N=$(python -c "import torch; print(torch.cuda.device_count())")
+           for impl in ours reference; do
+             NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL,TUNING timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+               tools/train_step_bench.py --impl $impl --steps 4 --warmup 2 > gpurun_out/${tag}_train_${impl}_n${N}.log 2>&1
+             grep '"what"' gpurun_out/${tag}_train_${impl}_n${N}.log | tee gpurun_out/${tag}_train_${impl}_n${N}.json
+             grep -E "NVLS|Ring|Tree|Algo|algo" gpurun_out/${tag}_train_${impl}_n${N}.log | sort | uniq -c | sort -rn | head -8 > gpurun_out/${tag}_train_${impl}_n${N}_nccl.txt
+             head -4 gpurun_out/${tag}_train_${impl}_n${N}_nccl.txt; tail -3 gpurun_out/${tag}_train_${impl}_n${N}.log | cut -c1-300
+           done ;;
+    config3) N=$(python -c "import torch; print(torch.cuda.device_count())")
+           timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 5 --warmup 3 --config3 \
+             > gpurun_out/${tag}_bench_config3_n${N}.json 2> gpurun_out/${tag}_bench_config3_n${N}.err; tail -2 gpurun_out/${tag}_bench_config3_n${N}.err | cut -c1-300
+           python -c "import json; d=json.loads(open('gpurun_out/${tag}_bench_config3_n${N}.json').read().strip().splitlines()[-1]); print(d['n_gpus'], round(d['value'],1), 'frames/s', d['config3'])" ;;
     bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-1500 gpurun_out/${tag}_bench.json ;;
     ncu)   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
              --profile-from-start off --csv --log-file gpurun_out/${tag}_launches.csv python tools/profile_seq.py > gpurun_out/${tag}_ncu.log 2>&1
