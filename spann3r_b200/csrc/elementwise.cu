@@ -233,21 +233,22 @@ int launch_im2col_3x3s2(const __nv_bfloat16* ihi, const __nv_bfloat16* ilo, int 
 // follows ATen's upsample_bilinear2d (scale = (in-1)/(out-1); src = scale*dst; lambda1 = src - floor).
 // ------------------------------------------------------------------------------------------------
 // Grid: x = 256-thread slabs of one output row's (pixel, 4-channel group) items, y = output row, z = image: the row
-// quantities (h0, vertical weights) are per block, the per-item index math is one 32-bit divide (a shift when C/4 is a power
+// quantities (h0, vertical weights) are per block, the per-item index math is one 32-bit divide (a shift when C/8 is a power
 // of two: C = 128 / 256 on this path).  Round 1's flat 64-bit index (five 64-bit div / mod per item) ran at 0.20 of the
 // HBM peak.  The 4 source float4 of neighbouring items overlap and come from L1 / L2.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, int H, int W, int C, float* __restrict__ out,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Ho,
-                                                         int Wo, int c4_shift) {
+                                                         int Wo, int c8_shift) {
   pdl_launch_dependents();
   pdl_wait();
   // (Ho, Wo) <= (2H, 2W): the output may be cropped (dust3r/heads/dpt_head.py:56 crops refinenet4's output to the next
-  // level's size when the patch grid is odd); the interpolation grid is always that of the full 2H x 2W image
-  const int c4 = C >> 2;
+  // level's size when the patch grid is odd); the interpolation grid is always that of the full 2H x 2W image.
+  // One item = one output pixel x 8 channels: eight 16-byte loads in flight per thread, 16-byte plane stores.
+  const int c8 = C >> 3;
   const unsigned item = blockIdx.x * 256u + threadIdx.x;
-  if (item >= (unsigned)(Wo * c4)) return;
-  const int wo = c4_shift >= 0 ? (int)(item >> c4_shift) : (int)(item / (unsigned)c4);
-  const int c = (int)(item - (unsigned)wo * (unsigned)c4) << 2;
+  if (item >= (unsigned)(Wo * c8)) return;
+  const int wo = c8_shift >= 0 ? (int)(item >> c8_shift) : (int)(item / (unsigned)c8);
+  const int c = (int)(item - (unsigned)wo * (unsigned)c8) << 3;
   const int ho = blockIdx.y, nb = blockIdx.z;
   const float sh = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float sw = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
@@ -256,38 +257,50 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
   const int hp = (h0 < H - 1) ? 1 : 0, wp = (w0 < W - 1) ? 1 : 0;
   const float h1l = hr - h0, h0l = 1.f - h1l, w1l = wr - w0, w0l = 1.f - w1l;
   const float* base = x + (((long long)nb * H + h0) * W + w0) * C + c;
-  const float4 v00 = *reinterpret_cast<const float4*>(base);
-  const float4 v01 = *reinterpret_cast<const float4*>(base + (long long)wp * C);
-  const float4 v10 = *reinterpret_cast<const float4*>(base + (long long)hp * W * C);
-  const float4 v11 = *reinterpret_cast<const float4*>(base + (long long)hp * W * C + (long long)wp * C);
-  float4 y;
-  y.x = h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x);
-  y.y = h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y);
-  y.z = h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z);
-  y.w = h0l * (w0l * v00.w + w1l * v01.w) + h1l * (w0l * v10.w + w1l * v11.w);
+  float4 v[4][2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    v[0][k] = *reinterpret_cast<const float4*>(base + 4 * k);
+    v[1][k] = *reinterpret_cast<const float4*>(base + (long long)wp * C + 4 * k);
+    v[2][k] = *reinterpret_cast<const float4*>(base + (long long)hp * W * C + 4 * k);
+    v[3][k] = *reinterpret_cast<const float4*>(base + (long long)hp * W * C + (long long)wp * C + 4 * k);
+  }
+  float4 y[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    y[k].x = h0l * (w0l * v[0][k].x + w1l * v[1][k].x) + h1l * (w0l * v[2][k].x + w1l * v[3][k].x);
+    y[k].y = h0l * (w0l * v[0][k].y + w1l * v[1][k].y) + h1l * (w0l * v[2][k].y + w1l * v[3][k].y);
+    y[k].z = h0l * (w0l * v[0][k].z + w1l * v[1][k].z) + h1l * (w0l * v[2][k].z + w1l * v[3][k].z);
+    y[k].w = h0l * (w0l * v[0][k].w + w1l * v[1][k].w) + h1l * (w0l * v[2][k].w + w1l * v[3][k].w);
+  }
   const long long o = (((long long)nb * Ho + ho) * Wo + wo) * C + c;
-  if (out) *reinterpret_cast<float4*>(out + o) = y;
+  if (out) {
+    *reinterpret_cast<float4*>(out + o) = y[0];
+    *reinterpret_cast<float4*>(out + o + 4) = y[1];
+  }
   if (hi) {
-    uint32_t h01, l01, h23, l23;
-    split2_bf16(y.x, y.y, h01, l01);
-    split2_bf16(y.z, y.w, h23, l23);
-    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h01, h23);
-    *reinterpret_cast<uint2*>(lo + o) = make_uint2(l01, l23);
+    uint32_t h[4], l[4];
+    split2_bf16(y[0].x, y[0].y, h[0], l[0]);
+    split2_bf16(y[0].z, y[0].w, h[1], l[1]);
+    split2_bf16(y[1].x, y[1].y, h[2], l[2]);
+    split2_bf16(y[1].z, y[1].w, h[3], l[3]);
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
 int launch_upsample2x(const float* x, int NB, int H, int W, int C, float* out, __nv_bfloat16* hi, __nv_bfloat16* lo,
                       cudaStream_t st, int Ho, int Wo) {
-  if (C % 4) { set_error("upsample2x: C %% 4 != 0"); return -1; }
+  if (C % 8) { set_error("upsample2x: C %% 8 != 0"); return -1; }
   if (Ho <= 0) Ho = 2 * H;
   if (Wo <= 0) Wo = 2 * W;
   if (Ho > 2 * H || Wo > 2 * W) { set_error("upsample2x: output %dx%d larger than 2x input", Ho, Wo); return -1; }
   if (NB <= 0 || Ho == 0 || Wo == 0) return 0;
   if (Ho > 65535 || NB > 65535) { set_error("upsample2x: %d rows x %d images exceed the grid limits", Ho, NB); return -1; }
-  const int c4 = C / 4;
+  const int c8 = C / 8;
   int shift = -1;
-  if ((c4 & (c4 - 1)) == 0) { shift = 0; while ((1 << shift) < c4) ++shift; }
-  const dim3 grid((unsigned)((Wo * c4 + 255) / 256), (unsigned)Ho, (unsigned)NB);
+  if ((c8 & (c8 - 1)) == 0) { shift = 0; while ((1 << shift) < c8) ++shift; }
+  const dim3 grid((unsigned)((Wo * c8 + 255) / 256), (unsigned)Ho, (unsigned)NB);
   launch_pdl(upsample2x_kernel, grid, dim3(256), 0, st, x, H, W, C, out, hi, lo, Ho, Wo, shift);
   return cudaGetLastError() == cudaSuccess ? 0 : -6;
 }

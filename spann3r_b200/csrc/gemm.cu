@@ -449,6 +449,9 @@ int gemm_plan_init(GemmPlan* plan, const __nv_bfloat16* a_hi, const __nv_bfloat1
   // per-tile epilogue preambles (LayerNorm statistics, staged columns) -- measured in situ, not visible in the sweep
   const long long tiles128 = m_tiles * nt128;
   if (two && taps == 1 && N % 256 == 0 && tiles128 >= 400) bn = 256;
+  // (Tried in round 2 and removed: 256 x 256 pair tiles for few-wave GEMMs whose last 256 x 128 wave is badly filled -- the
+  // decoder's / value encoder's fc1 at B = 1 -- one wave at 4/3 of the bytes per SM instead of two: +1.8 % per sequence in the
+  // in-process A/B, profiles/r2g_ab_256.jsonl.  Three ring slots of 64 KB do not cover the TMA latency of a one-wave launch.)
   if (force_bn == 0 && legal2 && (g2_mode == 128 || g2_mode == 256)) {
     two = 1;
     bn = (g2_mode == 256 && N % 256 == 0) ? 256 : 128;

@@ -98,7 +98,9 @@ struct Options {
                         // stages half of B.  In-process A/B on a B200: -1.8 % per sequence (profiles/r2b_ab_inproc.jsonl)
   int prefetch_b = 1;   // stage the first weight tiles before griddepcontrol.wait
   int attn_pair = 1;    // two query tiles per CTA for many-wave attention launches
-  int chain = 1;        // dependent GEMM runs of a block (proj -> fc1 -> fc2 -> next qkv, ...) as one persistent launch
+  int chain = 0;        // dependent GEMM runs of a block (proj -> fc1 -> fc2 -> next qkv, ...) as ONE persistent launch
+                        // (gemm_chain.cu).  Verified bit-identical to separate launches, but measured SLOWER on a B200 in three
+                        // builds (in-process A/B: +9 .. +15 % per sequence, profiles/r2_chain.md): off by default
 };
 Options& options();
 int num_sms();

@@ -258,46 +258,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gc::kThreads, 1)
         const int brow = t.g * a.b_group_rows + t.nt * bn + (int)rank * (bn / 2);
         const uint32_t* dep = (ph[p].dep >= 0) ? ctr + ph[ph[p].dep].ctr_base + t.ga * (a.tiles_w * a.tiles_h * a.NB) + t.mt
                                                : nullptr;
-        // weights first: the B tiles of the first ring pass go out before the dependency wait
-        const int pre = num_kb < stages ? num_kb : stages;
-        int st2 = stage;
-        uint32_t ph2 = phase;
-        for (int kb = 0; kb < pre; ++kb) {
-          mbar_wait(&empty_bar[st2], ph2 ^ 1);
+        // Per k-block: wait for the slot, issue the WEIGHT (B) tiles at once, and issue the A tiles as soon as the row block
+        // this tile depends on is complete.  One probe up front: in a many-wave phase the dependency is long satisfied and
+        // the loop is exactly the standalone kernel's (A and B together, slot by slot -- a first version issued a whole ring
+        // pass of B before any A and so drained the ring at EVERY tile boundary: +2.5 us per tile).  While it is not
+        // satisfied (single-wave phases) B runs ahead by up to one ring pass, then the producer blocks on the counter.
+        bool ready = true;
+        if (dep) {
+          uint32_t seen = 0;
+          if (lane == 0) seen = ld_acquire_gpu(dep);
+          ready = __shfl_sync(0xffffffffu, seen, 0) >= (uint32_t)ph[p].dep_need;
+        }
+        int a_next = 0, a_stage = stage;                   // next k-block whose A tiles are still to be issued, and its slot
+        const int run_ahead = num_kb < stages ? num_kb : stages;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
-            const uint32_t s = smem_u + st2 * stage_bytes;
-            const uint32_t fb = full_u + st2 * 8;
+            const uint32_t s = smem_u + stage * stage_bytes;
+            const uint32_t fb = full_u + stage * 8;
             if (leader) mbar_arrive_expect_tx_u(fb, tx);
-            else c_arrive_remote(&full_bar[st2], 0);
+            else c_arrive_remote(&full_bar[stage], 0);
             c_tma2_3d(s + 2 * A_TILE, &ag->tmB_hi, fb, kb * BK, 0, brow);
             c_tma2_3d(s + 2 * A_TILE + b_tile, &ag->tmB_lo, fb, kb * BK, 0, brow);
           }
           __syncwarp();
-          if (++st2 == stages) { st2 = 0; ph2 ^= 1; }
-        }
-        if (dep) {
-          // No proxy fence HERE: a fence.proxy.async after the B loads above drains them (measured: +2.5 us per tile, the
-          // whole chain 15 % slower than separate launches).  The generic -> async hand-over is fenced on the WRITER side,
-          // by the threads that stored the rows (below), before their release -- the same placement as a TMA-store epilogue.
-          if (lane == 0) dep_wait(dep, (uint32_t)ph[p].dep_need);
-          __syncwarp();
-        }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (kb >= pre) mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (elect_one()) {
-            const uint32_t s = smem_u + stage * stage_bytes;
-            const uint32_t fb = full_u + stage * 8;
-            if (kb >= pre) {
-              if (leader) mbar_arrive_expect_tx_u(fb, tx);
-              else c_arrive_remote(&full_bar[stage], 0);
-              c_tma2_3d(s + 2 * A_TILE, &ag->tmB_hi, fb, kb * BK, 0, brow);
-              c_tma2_3d(s + 2 * A_TILE + b_tile, &ag->tmB_lo, fb, kb * BK, 0, brow);
-            }
-            c_tma2_4d(s, &ag->tmA_hi, fb, kb * BK, row0, 0, t.ga);
-            c_tma2_4d(s + A_TILE, &ag->tmA_lo, fb, kb * BK, row0, 0, t.ga);
-          }
-          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (!ready) {
+            if (kb + 1 - a_next >= run_ahead || kb + 1 == num_kb) {   // the ring is full of B tiles (or all are out): block
+              if (lane == 0) dep_wait(dep, (uint32_t)ph[p].dep_need);
+              __syncwarp();
+              ready = true;
+            } else {
+              uint32_t seen = 0;
+              if (lane == 0) seen = ld_acquire_gpu(dep);
+              ready = __shfl_sync(0xffffffffu, seen, 0) >= (uint32_t)ph[p].dep_need;
+            }
+          }
+          if (ready) {
+            for (; a_next <= kb; ++a_next) {
+              if (elect_one()) {
+                const uint32_t s = smem_u + a_stage * stage_bytes;
+                const uint32_t fb = full_u + a_stage * 8;
+                c_tma2_4d(s, &ag->tmA_hi, fb, a_next * BK, row0, 0, t.ga);
+                c_tma2_4d(s + A_TILE, &ag->tmA_lo, fb, a_next * BK, row0, 0, t.ga);
+              }
+              __syncwarp();
+              if (++a_stage == stages) a_stage = 0;
+            }
+          }
         }
       }
     }

@@ -24,6 +24,7 @@ for step in "$@"; do
            cat gpurun_out/${tag}_ab_inproc.jsonl; tail -2 gpurun_out/${tag}_ab_inproc.err ;;
     chain) timeout 600 python -m pytest tests/test_chain_gpu.py -q -m gpu -x -s > gpurun_out/${tag}_chain_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_chain_tests.log; tail -30 gpurun_out/${tag}_chain_tests.log | cut -c1-400 ;;
     stages) for c in 0 1; do echo "S3R_CHAIN=$c"; S3R_CHAIN=$c timeout 300 python tools/stage_times.py 2>/dev/null | tee -a gpurun_out/${tag}_stage_times_chain$c.json; done ;;
+    ab256) timeout 600 python tools/ab_inproc.py gemm2_256=0,1 --rounds 12 > gpurun_out/${tag}_ab_256.jsonl 2> gpurun_out/${tag}_ab_256.err; cat gpurun_out/${tag}_ab_256.jsonl; tail -2 gpurun_out/${tag}_ab_256.err ;;
     abchain) timeout 600 python tools/ab_inproc.py chain=0,1 --rounds 12 > gpurun_out/${tag}_ab_chain.jsonl 2> gpurun_out/${tag}_ab_chain.err; cat gpurun_out/${tag}_ab_chain.jsonl; tail -2 gpurun_out/${tag}_ab_chain.err ;;
     train) timeout 900 python -m pytest tests/test_train_gpu.py tests/test_model_gpu.py -q -m gpu -k "train or raw or dropout or backward" -s > gpurun_out/${tag}_train_tests.log 2>&1
            echo "pytest exit $?" >> gpurun_out/${tag}_train_tests.log; tail -25 gpurun_out/${tag}_train_tests.log ;;

@@ -56,6 +56,6 @@ if "--traffic" in sys.argv:
     json.dump({"kernel": "gemm_bf16x3_kernel<*> + gemm2_bf16x3_kernel<*> (all launches of one 10-frame 512x384 sequence)",
                "launches": len(g), "dram_bytes_per_launch": (rd + wr) / max(len(g), 1), "dram_read_bytes_total": rd,
                "dram_write_bytes_total": wr,
-               "algorithmic_bytes_note": "weights 2.63 GB per frame-step are the compulsory HBM traffic: 25 GB / sequence",
+               "algorithmic_bytes_note": "compulsory HBM bytes of one sequence with the batched encoder: weights 1.21 GB (encoder, read once per sequence: all 10 frames in one M = 7680 call) + 9 x 1.42 GB (decoder, heads, value encoder per step) = 14.0 GB, plus ~1.3 GB per step of unfused DPT activations (SURVEY 8d) = 25.7 GB; the measured total is ~1.55x that and runs at ~12 % of the measured HBM peak: not the limiter",
                "source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum ({path})"},
               open(out, "w"), indent=1)
