@@ -72,27 +72,55 @@ __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restric
     for (int i = 1; i < 8; ++i) x = is_max ? fmaxf(x, red[i]) : x + red[i];
     return x;
   };
+  // Three passes over the row held in shared memory, 128-bit everywhere (the S row and both plane rows are 16-byte aligned:
+  // ldS / ldP are multiples of 32); the M % 4 tail, if any, is scalar.
+  const int M4 = M >> 2;
+  float4* row4 = reinterpret_cast<float4*>(row);
+  const float4* s4 = reinterpret_cast<const float4*>(s);
   float mx = -INFINITY;
-  for (int i = tid; i < M; i += 256) {
+  for (int i = tid; i < M4; i += 256) {
+    float4 v = s4[i];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    row4[i] = v;
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int i = 4 * M4 + tid; i < M; i += 256) {
     const float v = s[i] * scale;
     row[i] = v;
     mx = fmaxf(mx, v);
   }
   mx = block_reduce(mx, true);
   float sum = 0.f;
-  for (int i = tid; i < M; i += 256) {
+  for (int i = tid; i < M4; i += 256) {
+    float4 v = row4[i];
+    v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);
+    row4[i] = v;
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  for (int i = 4 * M4 + tid; i < M; i += 256) {
     const float e = expf(row[i] - mx);
     row[i] = e;
     sum += e;
   }
   sum = block_reduce(sum, false);
   const float inv = 1.0f / sum;
-  float sum2 = 0.f;
-  for (int i = tid; i < M; i += 256) {
-    float a = row[i] * inv;
+  const unsigned long long row_base = (unsigned long long)r * (unsigned long long)M;
+  auto weight = [&](float e, int i) -> float {
+    float a = e * inv;
     // dropout BEFORE the threshold, as in the reference (training runs with attn_thresh = 0)
-    if (drop_p > 0.f) a *= dropout_scale(seed, (unsigned long long)r * (unsigned long long)M + i, drop_p, keep_scale);
+    if (drop_p > 0.f) a *= dropout_scale(seed, row_base + i, drop_p, keep_scale);
     if (thresh > 0.f && a < thresh) a = 0.f;
+    return a;
+  };
+  float sum2 = 0.f;
+  for (int i = tid; i < M4; i += 256) {
+    float4 v = row4[i];
+    v.x = weight(v.x, 4 * i); v.y = weight(v.y, 4 * i + 1); v.z = weight(v.z, 4 * i + 2); v.w = weight(v.w, 4 * i + 3);
+    row4[i] = v;
+    sum2 += (v.x + v.y) + (v.z + v.w);
+  }
+  for (int i = 4 * M4 + tid; i < M; i += 256) {
+    const float a = weight(row[i], i);
     row[i] = a;
     sum2 += a;
   }
@@ -100,16 +128,27 @@ __global__ void __launch_bounds__(256) mem_softmax_kernel(const float* __restric
   if (thresh > 0.f) {
     sum2 = block_reduce(sum2, false);
     inv2 = 1.0f / sum2;  // 0/0 -> NaN when the whole row was cut, as in the reference
+  } else {
+    __syncthreads();     // the plane pass below reads other threads' entries
   }
   __nv_bfloat16* ph = phi + r * ldP;
   __nv_bfloat16* pl = plo + r * ldP;
-  for (int i = tid; i < Mpad; i += 256) {
-    float a = 0.f;
-    if (i < M) a = (thresh > 0.f) ? row[i] * inv2 : row[i];
-    __nv_bfloat16 h, l;
-    split_bf16(a, h, l);
-    ph[i] = h;
-    pl[i] = l;
+  const int P4 = Mpad >> 2;   // Mpad is a multiple of 8
+  for (int i = tid; i < P4; i += 256) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < M4) {
+      v = row4[i];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * i + j < M) (&v.x)[j] = row[4 * i + j];
+    }
+    if (thresh > 0.f) { v.x *= inv2; v.y *= inv2; v.z *= inv2; v.w *= inv2; }
+    uint32_t h01, l01, h23, l23;
+    split2_bf16(v.x, v.y, h01, l01);
+    split2_bf16(v.z, v.w, h23, l23);
+    *reinterpret_cast<uint2*>(ph + 4 * i) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(pl + 4 * i) = make_uint2(l01, l23);
   }
 }
 

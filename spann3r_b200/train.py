@@ -70,7 +70,7 @@ class _Stage(torch.autograd.Function):
         grads = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True)
         it = iter(grads)
         g_acts = [next(it) if t.requires_grad else None for t in acts]
-        g_params = list(it)
+        g_params = [g if g is None else g.contiguous() for g in it]   # DDP's buckets expect the parameters' own (dense) strides
         return (None, None, None, None, *g_acts, *g_params)
 
 

