@@ -152,6 +152,7 @@ def run_reference(args):
     if rank != 0:
         return
     from spann3r_b200 import synth
+    torch.set_num_threads(_host_threads())      # torchrun exports OMP_NUM_THREADS=1; constructing the reference is CPU work too
     sd = synth.make_state_dict(sharpen=True)
     m, why = _reference_model(sd)
     cpu = _cpu_reference_leg(sd, m, budget_s=100.0, max_steps=max(1, args.steps))
@@ -279,6 +280,9 @@ def main():
         return run_reference(args)
 
     rank, world, local = _dist()
+    # torchrun exports OMP_NUM_THREADS=1: the one-time host work of every rank (synthetic checkpoint, weight packing, and on
+    # rank 0 the baseline legs) gets this rank's share of the host cores instead of one thread
+    torch.set_num_threads(max(1, _host_threads() // max(world, 1)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

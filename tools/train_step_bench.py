@@ -60,6 +60,10 @@ def main():
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:     # torchrun exports OMP_NUM_THREADS=1: building the models is host work, give each rank its share of the cores
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // 2 // max(world, 1)))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from baseline import ref_loader
