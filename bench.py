@@ -162,9 +162,9 @@ def run_reference(args):
         "impl": "reference", "metric": "frames/sec (512x384, 10-frame seq) enc->mem-attn->dec->DPT", "value": cpu["value"],
         "unit": "frames/s", "n_gpus": args.gpus, "steps": cpu["steps"], "warmup": 1, "ms_per_step": cpu["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{FRAMES}-frame {WIDTH}x{HEIGHT} sequence per step, batch 1, ViT-L enc / ViT-B dec + DPT, "
-                               f"random-init sharpened checkpoint (SURVEY.md §8d config 2)",
-                   "parallelism": "host CPU, rank 0 only"},
+        "config": {"workload": f"{FRAMES}-frame {WIDTH}x{HEIGHT} sequence per step, batch 1 per GPU, ViT-L enc / ViT-B dec + DPT, "
+                               f"random-init sharpened checkpoint (SURVEY.md §8d config 2)",      # the CUDA arm's workload, verbatim
+                   "parallelism": "host CPU cores, rank 0 only (the reference's CPU path)"},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
