@@ -400,11 +400,9 @@ class Spann3R(ParamModule):
     def forward(self, frames, return_memory=False):
         """spann3r/model.py:473-539.  Eval mode: the inference path below.  Training mode (`self.training`): the same CUDA
         forward with the reference's training branches and a PyTorch-recompute backward (`train.py`)."""
-        if self.training and torch.is_grad_enabled():
+        if self.training:      # also under torch.no_grad(): the training BRANCHES are what .train() selects, as in the reference
             from .train import forward_train
             return forward_train(self, frames, return_memory)
-        if self.training:
-            raise RuntimeError("Spann3R is in training mode but autograd is disabled: call .eval() for inference")
         return self._forward_eval(frames, return_memory)
 
     @torch.no_grad()

@@ -32,13 +32,13 @@ _STAGE_PREFIXES = {
 
 
 def stage_params(model, stage: str):
-    """(names, parameters) of one stage, aliases (scratch.layerK_rn == scratch.layer_rn.K-1) listed once."""
-    names, params, seen = [], [], set()
+    """(names, parameters) of one stage, in state-dict order.  Aliased keys (scratch.layerK_rn == scratch.layer_rn.K-1) appear
+    under both names with the same Parameter; the restatement reads only `layer_rn.K-1`, the other input gets no gradient."""
+    names, params = [], []
     for n, p in model.named_parameters(remove_duplicate=False):
         if n.startswith(_STAGE_PREFIXES[stage]):
             names.append(n)
             params.append(p)
-            seen.add(id(p))
     return names, params
 
 
@@ -82,9 +82,10 @@ class TrainMemory:
     """SpatialMemory in training mode: ungated `add_mem` (spann3r/model.py:80-95, 518-519) into the engine's bank for the
     native read, plus the autograd-tracked raw keys / values the read's backward differentiates through."""
 
-    def __init__(self, engine, drop_p: float):
+    def __init__(self, engine, drop_p: float, names, params):
         from .engine import MemoryBank
         self.engine, self.drop_p = engine, float(drop_p)
+        self.names, self.params = names, params            # norm_q / norm_k / norm_v
         self.bank = None
         self.keys, self.vals = [], []
         self.MemoryBank = MemoryBank
@@ -98,9 +99,9 @@ class TrainMemory:
         self.keys.append(feat_k)
         self.vals.append(feat_v)
 
-    def memory_read(self, model, feat):
+    def memory_read(self, feat):
         mem_k, mem_v = torch.cat(self.keys, dim=1), torch.cat(self.vals, dim=1)
-        names, params = stage_params(model, "memread")
+        names, params = self.names, self.params
         p = self.drop_p
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0   # drawn from torch's CPU generator
         eng, bank = self.engine, self.bank
@@ -124,7 +125,7 @@ def forward_train(model, frames, return_memory=False):
     model._check_true_shape(frames, H, W)
     eng = model._engine_for(B, H, W, n_frames=F_, training=True)
     N = eng.N
-    mem = TrainMemory(eng, model.memory_dropout)
+    mem = TrainMemory(eng, model.memory_dropout, *stage_params(model, "memread"))
     imgs = [model._dev(f["img"]) for f in frames]
 
     enc_names, enc_params = stage_params(model, "encode")
@@ -150,7 +151,7 @@ def forward_train(model, frames, return_memory=False):
     preds, preds_all = None, []
     for i in range(F_ - 1):
         feat1, feat2 = feats[i], feats[i + 1]
-        feat_fuse = mem.memory_read(model, feat_k2) if feat_k2 is not None else feat1
+        feat_fuse = mem.memory_read(feat_k2) if feat_k2 is not None else feat1
         feat_k1, feat_k2, pts, conf = _apply(native_step, lambda P, a, b, c: R.step(P, a, b, c, H, W), step_names,
                                              step_params, feat_fuse, feat1, feat2)
         res1 = {"pts3d": pts[0], "conf": conf[0]}
