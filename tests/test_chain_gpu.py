@@ -24,7 +24,7 @@ def pair():
     try:
         yield _model(0), _model(1)     # plans are built lazily: every first call below sets the option again
     finally:
-        _lib.lib().s3r_set_option(b"chain", 1)
+        _lib.lib().s3r_set_option(b"chain", 0)      # the library default (the chain is off: profiles/r2_chain.md)
 
 
 @pytest.mark.parametrize("H,W,nimg", [(224, 224, 2), (384, 512, 2), (384, 512, 10), (224, 224, 5)])
