@@ -282,7 +282,8 @@ def main():
     rank, world, local = _dist()
     # torchrun exports OMP_NUM_THREADS=1: the one-time host work of every rank (synthetic checkpoint, weight packing, and on
     # rank 0 the baseline legs) gets this rank's share of the host cores instead of one thread
-    torch.set_num_threads(max(1, _host_threads() // max(world, 1)))
+    if os.environ.get("OMP_NUM_THREADS"):
+        torch.set_num_threads(max(1, _host_threads() // max(world, 1)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

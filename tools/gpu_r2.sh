@@ -20,6 +20,10 @@ for step in "$@"; do
            quick prefetch_off S3R_PREFETCH_B=0
            quick pair64 S3R_GEMM2_64=1
            quick base_again ;;
+    e2e)   quick plain
+           quick omp64 OMP_NUM_THREADS=64
+           quick omp1 OMP_NUM_THREADS=1
+           quick plain_again ;;
     abin)  timeout 600 python tools/ab_inproc.py gemm2_64=0,1 prefetch_b=0,1 attn_pair=0,1 --rounds 12 > gpurun_out/${tag}_ab_inproc.jsonl 2> gpurun_out/${tag}_ab_inproc.err
            cat gpurun_out/${tag}_ab_inproc.jsonl; tail -2 gpurun_out/${tag}_ab_inproc.err ;;
     chain) timeout 600 python -m pytest tests/test_chain_gpu.py -q -m gpu -x -s > gpurun_out/${tag}_chain_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_chain_tests.log; tail -30 gpurun_out/${tag}_chain_tests.log | cut -c1-400 ;;
