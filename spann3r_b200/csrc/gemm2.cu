@@ -134,6 +134,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  // optional timeline of CTA 0 (tools/trace_gemm2.py): [0] entry, [1] prologue done, [2] dependency wait done, [3] exit, then per
+  // tile it < 4 at [4 + 6 it]: first operands landed, all MMAs issued, accumulator seen by the epilogue, first chunk done,
+  // epilogue done, last k-block's loads issued
+  unsigned long long* const trace = (blockIdx.x == 0) ? args.trace : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
   const int n_tiles = (args.N + BN - 1) / BN;
   const int m_tiles = args.tiles_w * args.tiles_h * args.NB;   // even (host guarantees)
@@ -165,6 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
+  if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
   // B tiles of the first ring pass before the dependency wait (see gemm.cu): weights do not depend on the previous kernel
   int pre_b = 0;
   if (warp == 0 && args.b_static && cluster_id < total_pairs) {
@@ -187,6 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
     __syncwarp();
   }
   pdl_wait();
+  if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -196,7 +203,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
       const uint32_t full_u = __shfl_sync(0xffffffffu, smem_u32(full_bar), 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int pit = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++pit) {
         const int g = pt / pairs_per_group;
         const int rem = pt - g * pairs_per_group;
         const int mp = rem / n_tiles;
@@ -241,6 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
             phase ^= 1;
           }
         }
+        if (trace && pit < 4 && lane == 0) trace[4 + 6 * pit + 5] = globaltimer_ns();
       }
     }
   } else if (warp == 1) {
@@ -285,6 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         }
         if (elect_one()) umma2_commit_mc(&tmem_full[as]);        // accumulator ready in BOTH CTAs
         __syncwarp();
+        if (trace && it < 4 && lane == 0) trace[4 + 6 * it + 1] = globaltimer_ns();
       }
     }
   } else {
@@ -323,6 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
+      if (trace && it < 4 && threadIdx.x == 64) trace[4 + 6 * it + 2] = globaltimer_ns();
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
       float ht_acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -338,9 +349,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         epi_chunk<EPI, SW>(args, v, sb + c * 32, scs + c * 32, stg, tg, er, tr, rcur, col0, lane, ht_acc);
+        if (trace && it < 4 && cc == 0 && threadIdx.x == 64) trace[4 + 6 * it + 3] = globaltimer_ns();
 #pragma unroll
         for (int q = 0; q < 8; ++q) rcur[q] = rnxt[q];
       }
+      if (trace && it < 4 && threadIdx.x == 64) trace[4 + 6 * it + 4] = globaltimer_ns();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
@@ -370,6 +383,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
     tc_fence_after_sync();
     tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
   }
+  if (trace && threadIdx.x == 0) trace[3] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -56,6 +56,7 @@ for step in "$@"; do
            ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>> gpurun_out/${tag}_ncufull.log
            python tools/ncu_extract.py gpurun_out/${tag}_full_raw.csv --title "${tag}: ncu --set full, ${NCU_COUNT:-18} launches of the step phase (B=1, 512x384)" > gpurun_out/${tag}_ncu_full.md 2>> gpurun_out/${tag}_ncufull.log
            ls -la gpurun_out/${tag}_full.ncu-rep | cut -c20-80; head -12 gpurun_out/${tag}_ncu_full.md | cut -c1-260 ;;
+    trace2) timeout 300 python tools/trace_gemm2.py > gpurun_out/${tag}_trace_gemm2.txt 2> gpurun_out/${tag}_trace_gemm2.err; cat gpurun_out/${tag}_trace_gemm2.txt | cut -c1-400; tail -2 gpurun_out/${tag}_trace_gemm2.err ;;
     ltimes) timeout 300 python tools/launch_times.py > gpurun_out/${tag}_launch_times.json 2> gpurun_out/${tag}_launch_times.err; cat gpurun_out/${tag}_launch_times.json | cut -c1-1500; tail -2 gpurun_out/${tag}_launch_times.err ;;
     cfg4)  timeout 300 python bench.py --frames 100 --steps 2 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-raw > gpurun_out/${tag}_bench_config4.json 2> gpurun_out/${tag}_bench_config4.err
            python -c "import json; d=json.loads(open('gpurun_out/${tag}_bench_config4.json').read().strip().splitlines()[-1]); print('config 4 (100 frames):', round(d['value'],1), 'frames/s', round(d['ms_per_step'],1), 'ms per sequence, e2e', round(d['e2e']['value'],1))" ;;
