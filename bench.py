@@ -248,6 +248,10 @@ def _eager_gpu_legs(mref, why, sd, frames_dev, model, dev, F_):
                                                     "(kernels.cu:101 one-token patch): the reference's best shot"}
         except Exception as ex:
             eager["tf32_default_curope"] = {"unavailable": repr(ex)[:200]}
+        finally:     # hand the model back as it was built (the CPU leg runs the stock fallback)
+            mods = dict(mref.named_modules())
+            for name, r in locals().get("old", {}).items():
+                mods[name].rope = r
     return eager, parity
 
 
@@ -409,11 +413,9 @@ def main():
     if want_cpu or want_eager:
         sd_base = sd
         mref, why = _reference_model(sd_base)
-        if want_cpu:
-            # the reference's CPU path on the host cores: ONE full 10-frame 512x384 sequence (the headline config)
-            cpu = _cpu_reference_leg(sd_base, mref, budget_s=20.0, max_steps=1)
-            if mref is None:
-                cpu["note"] = why
+        # GPU legs FIRST: a CPU forward leaves the host's OpenMP pool spinning, which depresses whatever is timed on the GPU
+        # right after it (measured: the CUDA arm's own e2e drops from 195 to 138 frames/s under a 64-thread pool,
+        # profiles/r2k_e2e_threads.txt) -- the reference's eager-GPU numbers must not pay for its own CPU leg
         if want_eager:
             try:
                 eager, parity_ref = _eager_gpu_legs(mref, why, sd_base, resident[0], model, dev, F_)
@@ -422,6 +424,22 @@ def main():
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = False
                 torch.backends.cudnn.allow_tf32 = False
+        if want_cpu:
+            # the reference's CPU path on the host cores: ONE full 10-frame 512x384 sequence (the headline config)
+            try:
+                if mref is not None:
+                    mref = mref.cpu()
+                    for mod in mref.modules():                 # positions cached on the GPU by the legs above
+                        pg = getattr(mod, "position_getter", None)
+                        if pg is not None and hasattr(pg, "cache_positions"):
+                            pg.cache_positions = {}
+                        if hasattr(mod, "rope") and getattr(mod.rope, "cache", None) is not None:
+                            mod.rope.cache = {}
+                cpu = _cpu_reference_leg(sd_base, mref, budget_s=20.0, max_steps=1)
+                if mref is None:
+                    cpu["note"] = why
+            except Exception as ex:
+                cpu = {"unavailable": repr(ex)[:200]}
         del mref
 
     # ---- config 3 as written: 8 sequences per GPU through shard.run_sharded, lockstep and one by one ----

@@ -271,6 +271,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
+          if (trace && kb == 0 && it < 4 && lane == 0) trace[4 + 6 * it] = globaltimer_ns();
           if (elect_one()) {
             const uint32_t sa = smem_u + stage * Cfg::STAGE;
             const uint64_t da_hi = umma_desc_sw128_kmajor(sa);

@@ -39,14 +39,14 @@ for name, K, N, fbn, act in CASES:
     torch.cuda.synchronize()
     t = trace.cpu().double()
     print(f"{name}: CTA 0, ns relative to this launch's dependency-wait release (launches 8..11); tiles of CTA 0: "
-          f"{int((t[8, 4::6] > 0).sum())}")
+          f"{int((t[8, 5::6] > 0).sum())}")
     for i in range(8, 12):
         base = t[i, 2]
         head = f"   prev-exit->wait {t[i, 2] - t[i - 1, 3]:6.0f}  entry {t[i, 0] - base:7.0f}  exit {t[i, 3] - base:7.0f} |"
         tiles = []
         for it in range(4):
             s = t[i, 4 + 6 * it: 10 + 6 * it]
-            if s[0] == 0:
+            if s[1] == 0:
                 break
             tiles.append(f" T{it}: ops {s[0] - base:6.0f} mma_done {s[1] - base:6.0f} epi_start {s[2] - base:6.0f} chunk0 {s[3] - base:6.0f} "
                          f"epi_end {s[4] - base:6.0f} loads_out {s[5] - base:6.0f}")
