@@ -61,11 +61,13 @@ for step in "$@"; do
     cfg4)  timeout 300 python bench.py --frames 100 --steps 2 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-raw > gpurun_out/${tag}_bench_config4.json 2> gpurun_out/${tag}_bench_config4.err
            python -c "import json; d=json.loads(open('gpurun_out/${tag}_bench_config4.json').read().strip().splitlines()[-1]); print('config 4 (100 frames):', round(d['value'],1), 'frames/s', round(d['ms_per_step'],1), 'ms per sequence, e2e', round(d['e2e']['value'],1))" ;;
     ncusrc) # source-level stall profile of ONE fc1-sized launch (gemm2<128, EPI_PLAIN>) of the decoder: where do the epilogue warps wait?
-           timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:'gemm2_bf16x3_kernel<128, *0>' \
+           timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off --kernel-name-base demangled -k regex:'gemm2_bf16x3_kernel<.int.128, .int.0>' \
              --launch-skip ${NCU_SKIP:-8} --launch-count 1 -f -o gpurun_out/${tag}_src python tools/profile_seq.py 3 > gpurun_out/${tag}_ncusrc.log 2>&1
            ncu -i gpurun_out/${tag}_src.ncu-rep --page source --csv > gpurun_out/${tag}_src_page.csv 2>> gpurun_out/${tag}_ncusrc.log
            ncu -i gpurun_out/${tag}_src.ncu-rep --page raw --csv > gpurun_out/${tag}_src_raw.csv 2>> gpurun_out/${tag}_ncusrc.log
            ls -la gpurun_out/${tag}_src* | cut -c25-100; head -3 gpurun_out/${tag}_src_page.csv | cut -c1-400 ;;
+    b8)    timeout 400 python bench.py --batch 8 --steps 4 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-raw > gpurun_out/${tag}_bench_b8.json 2> gpurun_out/${tag}_bench_b8.err
+           python -c "import json; d=json.loads(open('gpurun_out/${tag}_bench_b8.json').read().strip().splitlines()[-1]); r=d['roofline']; print('B=8 lockstep, 1 GPU:', round(d['value'],1), 'frames/s', round(d['ms_per_step'],1), 'ms per 8 sequences; e2e', round(d['e2e']['value'],1), '; GEMM engine', round(r['achieved'],1), 'TFLOP/s frac', round(r['frac'],3), 'whole path', round(r['whole_path_frac'],3))" ;;
     smoke) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file gpurun_out/${tag}_smoke_launches.csv \
              python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
            python - <<PY
