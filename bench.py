@@ -42,10 +42,13 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe).  The process is started
+    BEFORE the warm-up (nvidia-smi needs ~0.3 s to deliver its first row; a 5-step run is over by then) and only the rows that
+    arrive inside [mark_begin, mark_end] -- the device-timed loop and the e2e loop -- are reported."""
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -59,18 +62,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0, t1 = self.t0 or 0.0, (self.t1 or time.time()) + 0.12     # a row describes the 100 ms before it arrives
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        window = "timed regions"
+        if not rows and self.rows:      # shorter than one sampling period: the last rows before the end (warm-up load)
+            rows, window = [r for _, r in self.rows[-3:]], "last rows before the end of the timed regions"
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def _dist():
@@ -327,17 +341,18 @@ def main():
         return shard.max_over_ranks(ms, device=dev)
 
     # ---- warm-up (also builds every tensor map / plan) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(W_):
         model(resident[i % n_distinct])
     eng = model._engine_for(BATCH, HEIGHT, WIDTH, n_frames=F_)
     torch.cuda.synchronize(dev)
 
     # ---- timed: inputs resident in HBM ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     eng.take_launches(); eng.take_flops()
     barrier()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
@@ -347,7 +362,6 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.take_launches()
     flops_issued = eng.take_flops()
-    clocks = sampler.stop() if rank == 0 else None
     value = world * BATCH * F_ * K / (ms / 1e3)
 
     # ---- timed: end to end through the public API, pinned host inputs -> device, predictions -> pinned host ----
@@ -371,6 +385,8 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     h2d = BATCH * F_ * 3 * HEIGHT * WIDTH * 4
     d2h = sum(o.numel() * 4 for o in outs)
     e2e = world * BATCH * F_ * K / (ms_e2e / 1e3)
