@@ -44,7 +44,7 @@ def _peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe).  The process is started
     BEFORE the warm-up (nvidia-smi needs ~0.3 s to deliver its first row; a 5-step run is over by then) and only the rows that
-    arrive inside [mark_begin, mark_end] -- the device-timed loop and the e2e loop -- are reported."""
+    arrive inside [mark_begin, mark_end] -- the device-timed loop -- are reported; it is stopped before the e2e loop."""
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
@@ -362,6 +362,10 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.take_launches()
     flops_issued = eng.take_flops()
+    # the sampler stops HERE: nvidia-smi polling the driver every 100 ms costs the e2e loop below a third of its throughput
+    # (135 vs 196 frames/s, profiles/r2q_bench.json vs r2m_bench.json) -- its queries serialise with the pinned-memory copies
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     value = world * BATCH * F_ * K / (ms / 1e3)
 
     # ---- timed: end to end through the public API, pinned host inputs -> device, predictions -> pinned host ----
@@ -385,8 +389,6 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    sampler.mark_end()
-    clocks = sampler.stop() if rank == 0 else None
     h2d = BATCH * F_ * 3 * HEIGHT * WIDTH * 4
     d2h = sum(o.numel() * 4 for o in outs)
     e2e = world * BATCH * F_ * K / (ms_e2e / 1e3)
@@ -413,7 +415,9 @@ def main():
         "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["bf16_sustained"],
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"],
         "note": "achieved = algorithmic 2MNK FLOPs / CUDA-event time summed over all GEMM/conv launches of one sequence; "
-                "the split-bf16 scheme issues 3 MMAs per product, so issued-MMA rate = 3x achieved (cap 1/3 of peak)",
+                "the split-bf16 scheme issues 3 MMAs per product, so issued-MMA rate = 3x achieved (cap 1/3 of peak).  The per-launch "
+                "times come from a SEPARATE profiling pass with CUDA events around every launch (no PDL overlap, DPT side streams "
+                "serialised), so gemm_ms_per_seq + attention_ms_per_seq exceeds ms_per_step: they are not in-situ times",
         "gemm_launches_per_seq": prof["gemm_launches"], "gemm_ms_per_seq": prof["gemm_ms"],
         "gemm_flops_per_launch": prof["gemm_flops"] / max(prof["gemm_launches"], 1),
         "attention_ms_per_seq": prof["attn_ms"], "attention_tflops": (prof["attn_flops"] / (prof["attn_ms"] * 1e-3) / 1e12
