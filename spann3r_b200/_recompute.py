@@ -14,11 +14,14 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from . import _native_linear
+
 ENC_HEADS, DEC_HEADS, VAL_HEADS = 16, 12, 16
 
 
 def _lin(P, n, x):
-    return F.linear(x, P[n + ".weight"], P[n + ".bias"])
+    # F.linear + PyTorch autograd by default; with the switch on, forward / dgrad / wgrad on the tcgen05 GEMM engine
+    return _native_linear.linear(x, P[n + ".weight"], P[n + ".bias"])
 
 
 def _ln(P, n, x, eps):

@@ -74,6 +74,13 @@ class _Stage(torch.autograd.Function):
         return (None, None, None, None, *g_acts, *g_params)
 
 
+def set_native_linear(on: bool = True):
+    """Run the Linear layers of the backward (recompute forward, dgrad, wgrad) on the tcgen05 GEMM engine (`_native_linear.py`)
+    instead of `F.linear` + PyTorch autograd."""
+    from . import _native_linear
+    _native_linear.ENABLED = bool(on)
+
+
 def _apply(native, torch_fn, names, params, *acts):
     return _Stage.apply(native, torch_fn, names, len(acts), *acts, *params)
 

@@ -120,3 +120,53 @@ def test_backward_gradients_vs_oracle_autograd(model):
     print({k: "%.1e" % v for k, v in errs.items()})
     assert max(errs.values()) < 3e-3, errs
     assert min(cos.values()) > 0.99999, cos
+
+
+def test_native_linear_forward_dgrad_wgrad_vs_torch():
+    """`_native_linear`: y = x W^T + b, dx = dy W, dW = dy^T x, db on the tcgen05 GEMM engine (bf16x3) against torch fp64,
+    incl. a row count that is not a multiple of 8 (the wgrad contraction is zero-padded) and the 1792-wide key head."""
+    from spann3r_b200 import _native_linear as NL
+    g = torch.Generator().manual_seed(3)
+    for lead, K, N in (((2, 196), 768, 3072), ((1, 588), 1024, 1024), ((3, 50), 1792, 1792), ((784,), 3072, 768)):
+        x = torch.randn(*lead, K, generator=g).cuda().requires_grad_(True)
+        w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().requires_grad_(True)
+        b = torch.randn(N, generator=g).cuda().requires_grad_(True)
+        gy = torch.randn(*lead, N, generator=g).cuda()
+        y = NL._NativeLinear.apply(x, w, b)
+        gx, gw, gb = torch.autograd.grad(y, (x, w, b), gy)
+        xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = torch.nn.functional.linear(xd, wd, bd)
+        rx, rw, rb = torch.autograd.grad(yr, (xd, wd, bd), gy.double())
+        for name, a, r in (("y", y, yr), ("dx", gx, rx), ("dW", gw, rw), ("db", gb, rb)):
+            assert a.shape == r.shape, name
+            assert rel_l2(a.detach().cpu(), r.detach().cpu()) < 3e-5, (lead, K, N, name, rel_l2(a.detach().cpu(), r.detach().cpu()))
+
+
+def test_backward_with_native_linear_matches_the_torch_backward(model):
+    """The same training step differentiated with the Linear layers of the backward on the GEMM engine (`set_native_linear`)
+    and with PyTorch's: the gradients agree to bf16x3 accuracy."""
+    from spann3r_b200 import synth, train
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    frames = synth.make_frames(3, 224, 224)
+    watch = ["dust3r.enc_blocks.3.attn.qkv.weight", "dust3r.dec_blocks.7.cross_attn.projk.weight", "dust3r.dec_blocks2.2.mlp.fc1.bias",
+             "attn_head_2.0.weight", "value_encoder.4.mlp.fc2.weight", "value_out.bias", "norm_k.weight",
+             "dust3r.downstream_head1.dpt.scratch.refinenet2.resConfUnit1.conv1.weight"]
+    named = dict(model.named_parameters())
+    grads = {}
+    try:
+        for native in (False, True):
+            train.set_native_linear(native)
+            model.train()
+            model.zero_grad(set_to_none=True)
+            preds, _ = model(frames)
+            loss = sum(p[k].square().mean() + p["conf"].log().mean() for p in preds for k in p if k != "conf")
+            loss.backward()
+            grads[native] = {k: named[k].grad.detach().clone() for k in watch}
+    finally:
+        train.set_native_linear(False)
+        model.zero_grad(set_to_none=True)
+        model.eval()
+    errs = {k: rel_l2(grads[True][k].cpu(), grads[False][k].cpu()) for k in watch}
+    print({k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < 2e-4, errs

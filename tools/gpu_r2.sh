@@ -32,6 +32,8 @@ for step in "$@"; do
     abchain) timeout 600 python tools/ab_inproc.py chain=0,1 --rounds 12 > gpurun_out/${tag}_ab_chain.jsonl 2> gpurun_out/${tag}_ab_chain.err; cat gpurun_out/${tag}_ab_chain.jsonl; tail -2 gpurun_out/${tag}_ab_chain.err ;;
     train) timeout 900 python -m pytest tests/test_train_gpu.py tests/test_model_gpu.py -q -m gpu -k "train or raw or dropout or backward" -s > gpurun_out/${tag}_train_tests.log 2>&1
            echo "pytest exit $?" >> gpurun_out/${tag}_train_tests.log; tail -25 gpurun_out/${tag}_train_tests.log ;;
+    nativelin) timeout 600 python -m pytest tests/test_train_gpu.py -q -m gpu -k "native_linear" -s > gpurun_out/${tag}_native_linear_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_native_linear_tests.log; tail -12 gpurun_out/${tag}_native_linear_tests.log | cut -c1-300
+           for v in 0 1; do S3R_TRAIN_NATIVE_LINEAR=$v timeout 400 python tools/train_step_bench.py --impl ours --steps 3 --warmup 2 2> gpurun_out/${tag}_train1_native$v.err | grep '"what"' | tee gpurun_out/${tag}_train1_native$v.json | cut -c1-700; done ;;
     trainbench) # config 5 on the GPUs of this call (N = CUDA device count): ours, then the reference, NCCL algorithm from its log
            N=$(python -c "import torch; print(torch.cuda.device_count())")
            for impl in ours reference; do
